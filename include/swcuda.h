@@ -1,0 +1,274 @@
+/*
+ * swcuda.h -- C ABI of libswcuda.so: the B200-native (sm_100a) kernel layer for the fp64
+ * shallow-water time step of Andrcraft9/ocean_model_arch.
+ *
+ * This is the drop-in boundary.  A reference maintainer binds these entry points from Fortran
+ * with iso_c_binding (see INTEGRATION.md and fortran/sw_interface_cuda.f90) in place of the
+ * per-block kernel envokes of interface/shallow_water/sw_interface.f90 and the CUDA-Fortran
+ * launch wrappers of gpu/interface/sw_interface_gpu.f90.  All `file:line` citations are relative
+ * to the reference repository root.
+ *
+ * Conventions
+ *   - plain C types only; `int` is 32-bit like Fortran's default integer;
+ *   - arrays are the reference's explicit-shape block arrays A(bnd_x1:bnd_x2, bnd_y1:bnd_y2),
+ *     column-major, m (x) contiguous: element (m,n) at
+ *     base[(n-bnd_y1)*(bnd_x2-bnd_x1+1) + (m-bnd_x1)]  (core/decomposition.f90:493-503);
+ *   - real(8) -> double, real(4) -> float (masks, metrics, Coriolis, friction are real(4));
+ *   - every function returns SWCU_OK (0) or an error code; swcu_last_error() gives the text.
+ *     The reference ignores CUDA istat and aborts through abort_model (shared/errors.f90:30-37);
+ *     the Fortran shim calls abort_model on any non-zero return;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SWCU_ERR_CUDA.
+ */
+#ifndef SWCUDA_H
+#define SWCUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWCU_OK 0
+#define SWCU_ERR_CUDA 1   /* CUDA runtime error (text in swcu_last_error) */
+#define SWCU_ERR_ARG 2    /* bad argument / unknown field id */
+#define SWCU_ERR_NCCL 3   /* NCCL error or NCCL library not loadable */
+#define SWCU_ERR_STATE 4  /* call not valid in the context's current mode/state */
+#define SWCU_ERR_BLOWUP 5 /* check_ssh_err found |ssh| >= 1e4 or NaN on a sea cell */
+
+/* The eight leading integer arguments of every reference kernel
+ * (e.g. kernel/shallow_water/vel_ssh.f90:69-72), i.e. domain%bnx_start(k) ... domain%bbnd_y2(k)
+ * as passed by the binders (interface/shallow_water/sw_interface.f90:46-47). */
+typedef struct swcu_dims {
+    int nx_start, nx_end, ny_start, ny_end;
+    int bnd_x1, bnd_x2, bnd_y1, bnd_y2;
+} swcu_dims;
+
+const char *swcu_last_error(void);
+int swcu_version(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int swcu_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Level A -- stateless 1:1 kernels on DEVICE pointers, reference argument order.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Launches are
+ * asynchronous.  Each replaces one CPU kernel / one CUDA-Fortran kernel of the reference:
+ * ------------------------------------------------------------------------------------------ */
+
+/* K1  kernel/shallow_water/vel_ssh.f90:69-106  (gpu/kernel/vel_ssh_gpu.f90:24-61) */
+int swcu_sw_update_ssh_kernel(const swcu_dims *d, double tau,
+        const float *lu, const float *dx, const float *dy, const float *dxh, const float *dyh,
+        const double *hhu, const double *hhv, double *sshn, const double *sshp,
+        const double *ubrtr, const double *vbrtr, void *stream);
+
+/* K7  kernel/shallow_water/vel_ssh.f90:108-195  (gpu/kernel/vel_ssh_gpu.f90:63-153) */
+int swcu_sw_update_uv(const swcu_dims *d, double tau, const float *lcu, const float *lcv,
+        const float *dxt, const float *dyt, const float *dxh, const float *dyh,
+        const float *dxb, const float *dyb,
+        const double *hhu, const double *hhun, const double *hhup,
+        const double *hhv, const double *hhvn, const double *hhvp,
+        const double *hhh, const double *ssh,
+        const double *ubrtr, double *ubrtrn, const double *ubrtrp,
+        const double *vbrtr, double *vbrtrn, const double *vbrtrp,
+        const float *rdis, const float *rlh_s,
+        const double *RHSx, const double *RHSy, const double *RHSx_adv, const double *RHSy_adv,
+        const double *RHSx_dif, const double *RHSy_dif, void *stream);
+
+/* K8  kernel/shallow_water/vel_ssh.f90:197-245  (gpu/kernel/vel_ssh_gpu.f90:155-203) */
+int swcu_sw_next_step(const swcu_dims *d, double time_smooth,
+        const float *lu, const float *lcu, const float *lcv,
+        double *ssh, double *sshn, double *sshp,
+        double *ubrtr, double *ubrtrn, double *ubrtrp,
+        double *vbrtr, double *vbrtrn, double *vbrtrp, void *stream);
+
+/* K3  kernel/shallow_water/vel_ssh.f90:247-281  (nlev = 1) */
+int swcu_uv_trans_vort_kernel(const swcu_dims *d, const float *luu,
+        const float *dxt, const float *dyt, const float *dxb, const float *dyb,
+        const double *u, const double *v, double *vort, void *stream);
+
+/* K4  kernel/shallow_water/vel_ssh.f90:283-373  (nlev = 1; hq is accepted and unused) */
+int swcu_uv_trans_kernel(const swcu_dims *d, const float *lcu, const float *lcv, const float *luu,
+        const float *dxh, const float *dyh, const double *u, const double *v, const double *vort,
+        const double *hq, const double *hu, const double *hv, const double *hh,
+        double *RHSx, double *RHSy, void *stream);
+
+/* K6  kernel/shallow_water/vel_ssh.f90:375-452  (nlev = 1; hu, hv accepted and unused) */
+int swcu_uv_diff2_kernel(const swcu_dims *d, const float *lcu, const float *lcv,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        const double *mu, const double *str_t, const double *str_s,
+        const double *hq, const double *hu, const double *hv, const double *hh,
+        double *RHSx, double *RHSy, void *stream);
+
+/* K5  kernel/shallow_water/mixing.f90:14-58  (nlev = 1) */
+int swcu_stress_components_kernel(const swcu_dims *d, const float *lu, const float *luu,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        const double *u, const double *v, double *str_t, double *str_s, void *stream);
+
+/* K10 kernel/shallow_water/depth.f90:14-99.  full_free_surface is a module variable in the
+ * reference (config_sw_module); here it is an argument.  sh, shp, h_r are read-only. */
+int swcu_hh_init_kernel(const swcu_dims *d, int full_free_surface,
+        const float *lu, const float *llu, const float *llv, const float *luh,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
+        double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn,
+        const double *sh, const double *shp, const double *h_r, void *stream);
+
+/* K2  kernel/shallow_water/depth.f90:101-162 */
+int swcu_hh_update_kernel(const swcu_dims *d,
+        const float *lu, const float *llu, const float *llv, const float *luh,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        double *hqn, double *hun, double *hvn, double *hhn,
+        const double *sh, const double *h_r, void *stream);
+
+/* K9  kernel/shallow_water/depth.f90:164-211.  time_smooth is a module variable in the
+ * reference; here it is an argument. */
+int swcu_hh_shift_kernel(const swcu_dims *d, double time_smooth,
+        const float *lu, const float *llu, const float *llv, const float *luh,
+        double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
+        double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn, void *stream);
+
+/* K11 kernel/shallow_water/vel_ssh.f90:40-67.  Instead of abort_model the number of offending
+ * sea cells is ADDED to *bad_count (a device int the caller zeroes). */
+int swcu_check_ssh_err_kernel(const swcu_dims *d, const float *lu, const double *ssh,
+        int *bad_count, void *stream);
+
+/* tracer kernels, kernel/tracer/leapfrog_tracer.f90:13-98, 100-141, 143-170 */
+int swcu_tran_diff_fluxes_kernel(const swcu_dims *d, const float *lcu, const float *lcv,
+        const float *dxt, const float *dyt, const float *dxh, const float *dyh,
+        const double *hhu, const double *hhv, const double *ff, const double *ffp,
+        const double *uu, const double *vv, const double *mu, double factor_mu,
+        double *flux_x, double *flux_y, void *stream);
+int swcu_tran_diff_tracer_kernel(const swcu_dims *d, const float *lu, const float *dx, const float *dy,
+        double tau, const double *hhqn, const double *hhqp,
+        const double *flux_x, const double *flux_y, const double *ffp, double *ffn, void *stream);
+int swcu_tracer_next_step_kernel(const swcu_dims *d, double time_smooth, const float *lu,
+        const double *ffn, double *ffp, double *ff, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Level B -- resident context: one block of the reference's decomposition lives on one GPU.
+ * Replaces field_device storage (core/data_types.f90:56-59), init_device_data
+ * (control/init_data.f90:127-145), expl_shallow_water_gpu (control/shallow_water/
+ * shallow_water.f90:184-251), expl_tracer and the mode-5 host-staged halo syncs
+ * (shared/mpp/sync.f90:378-536).  The library owns all device memory.
+ * ------------------------------------------------------------------------------------------ */
+
+/* field ids: every array of ocean_type (core/ocean.f90:14-48) and grid_type (core/grid.f90:23-90)
+ * that the shallow-water / tracer step touches */
+enum swcu_field {
+    /* real(8) */
+    SWCU_F_SSH = 0, SWCU_F_SSHN, SWCU_F_SSHP,
+    SWCU_F_UBRTR, SWCU_F_UBRTRN, SWCU_F_UBRTRP,
+    SWCU_F_VBRTR, SWCU_F_VBRTRN, SWCU_F_VBRTRP,
+    SWCU_F_RHSX, SWCU_F_RHSY, SWCU_F_RHSX_ADV, SWCU_F_RHSY_ADV, SWCU_F_RHSX_DIF, SWCU_F_RHSY_DIF,
+    SWCU_F_MU, SWCU_F_STR_T, SWCU_F_STR_S, SWCU_F_VORT,
+    SWCU_F_HHQ_REST, SWCU_F_HHQ, SWCU_F_HHQ_P, SWCU_F_HHQ_N,
+    SWCU_F_HHU, SWCU_F_HHU_P, SWCU_F_HHU_N, SWCU_F_HHV, SWCU_F_HHV_P, SWCU_F_HHV_N,
+    SWCU_F_HHH, SWCU_F_HHH_P, SWCU_F_HHH_N,
+    SWCU_F_FLUX_X, SWCU_F_FLUX_Y, SWCU_F_FF1, SWCU_F_FF1N, SWCU_F_FF1P,
+    SWCU_NF8,
+    /* real(4) */
+    SWCU_F_LU = 100, SWCU_F_LUU, SWCU_F_LUH, SWCU_F_LCU, SWCU_F_LCV, SWCU_F_LLU, SWCU_F_LLV,
+    SWCU_F_DX, SWCU_F_DY, SWCU_F_DXT, SWCU_F_DYT, SWCU_F_DXH, SWCU_F_DYH, SWCU_F_DXB, SWCU_F_DYB,
+    SWCU_F_RLH_S, SWCU_F_R_DISS,
+    SWCU_F4_END
+};
+#define SWCU_NF4 (SWCU_F4_END - 100)
+
+/* step structure */
+#define SWCU_MODE_REFERENCE 0 /* the reference's 11-kernel sequence, one launch per kernel (K1..K11) */
+#define SWCU_MODE_FUSED 1     /* 2 launches per step: depth/vorticity/stress prep + update/filter */
+
+typedef struct swcu_params {
+    int full_free_surface, trans_terms, ksw_lat; /* sw.par 1-3 (configs/sw.f90:34-36) */
+    double time_smooth;                          /* sw.par 4 */
+    int use_tracers;                             /* sw.par 6 (0/1; one tracer field, ff1(1)) */
+    int mode;                                    /* SWCU_MODE_* */
+} swcu_params;
+
+typedef struct swcu_ctx swcu_ctx;
+
+/* Creates the context on CUDA device `device` for one block.  All fields start zero-filled, like
+ * the reference's allocations (core/data_types.f90:529). */
+int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params, int device);
+int swcu_destroy(swcu_ctx *ctx);
+
+/* Host <-> device copies of one whole block array in the reference layout (host pointer =
+ * block(k)%field).  Replaces sync_host_device (core/data_types.f90:934-950).  In FUSED mode the
+ * derived fields (hh*, vort, str_*, RHS*_adv, RHS*_dif, sshn/ubrtrn/vbrtrn) are recomputed on demand by
+ * swcu_download from the resident state, giving the values the reference holds after the same
+ * number of steps. */
+int swcu_upload(swcu_ctx *ctx, int field, const void *host);
+int swcu_download(swcu_ctx *ctx, int field, void *host);
+/* Same, but the other side is a DEVICE pointer in the reference layout (for callers that keep
+ * their own device arrays, e.g. CUDA-Fortran field_device). */
+int swcu_upload_from_device(swcu_ctx *ctx, int field, const void *dev);
+int swcu_download_to_device(swcu_ctx *ctx, int field, void *dev);
+
+/* The envoke(hh_init) of init_ocean_data (control/init_data.f90:60-63): K10 + its halo sync on the
+ * resident arrays, to be called once after the initial uploads.  A no-op in FUSED mode, where the
+ * depth fields are functions of the resident state. */
+int swcu_envoke_hh_init(swcu_ctx *ctx);
+
+/* nsteps x expl_shallow_water(tau) [+ expl_tracer(tau) when use_tracers], asynchronous on the
+ * context's stream; no host round trip.  With a communicator attached (below) every step
+ * exchanges halos with the neighbouring blocks. */
+int swcu_step(swcu_ctx *ctx, double tau, int nsteps);
+/* Waits for the context's streams; returns SWCU_ERR_BLOWUP if K11 flagged cells since the last
+ * call (their count in *bad_cells when non-NULL). */
+int swcu_synchronize(swcu_ctx *ctx, long *bad_cells);
+
+/* Timing helpers on the context's stream (CUDA events), so host languages without a CUDA binding
+ * can time the step the way mpp_device_time_model_step does (shared/mpp/mpp.f90:406-423). */
+int swcu_timer_start(swcu_ctx *ctx);
+int swcu_timer_stop(swcu_ctx *ctx, float *elapsed_ms);
+/* Launch count of this library's kernels on this context since creation. */
+long swcu_launch_count(const swcu_ctx *ctx);
+/* Bytes of device memory held by the context. */
+long swcu_device_bytes(const swcu_ctx *ctx);
+/* The context's compute stream as a cudaStream_t (void*). */
+void *swcu_stream(swcu_ctx *ctx);
+
+/* Multi-GPU: one block per GPU, y-slab decomposition (parallel.par: bppnx = 1, bppny = nranks;
+ * core/decomposition.f90:468-486).  Replaces hybrid_sync / syncborder_data2D_real8
+ * (shared/mpp/sync.f90:294-374, syncborder_block2D_gen_all.fi) with ncclSend/ncclRecv of halo
+ * rows over NVLink on a side stream, overlapped with interior compute.
+ * swcu_comm_unique_id fills a 128-byte ncclUniqueId on one rank; the caller broadcasts it
+ * (MPI_Bcast in the Fortran host, torch.distributed in the Python host). */
+int swcu_comm_unique_id(void *id128);
+int swcu_comm_init(swcu_ctx *ctx, int nranks, int rank, const void *id128);
+int swcu_comm_destroy(swcu_ctx *ctx);
+/* One explicit halo exchange of a field (all ranks call it): the analogue of
+ * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use. */
+int swcu_halo_exchange(swcu_ctx *ctx, int field);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side input construction (C++, no GPU needed): what init_grid_data / init_ocean_data
+ * (control/init_data.f90:29-125) produce for one block, in the reference layout.  These mirror
+ * lu_init_kernel / lu_lv_init_kernel / grid_base_init_kernel / grid_geo_init_kernel
+ * (kernel/service/grid_kernels.f90:18-204, 206-538) and gaussian_elimination_kernel
+ * (kernel/shallow_water/vel_ssh.f90:15-38).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct swh_basin {
+    int nx, ny;                              /* basin.par 1-2 */
+    double dxst, dyst, rlon, rlat;           /* basin.par 6-9 */
+    int curve_grid;                          /* basin.par 12: 0 carthesian, 1 spherical */
+    double rotation_on_lon, rotation_on_lat; /* basin.par 13-14 */
+} swh_basin;
+
+/* mask: global nx*ny ints ((m,n) at mask[(n-1)*nx+(m-1)], 0 = sea) or NULL for "none". */
+int swh_masks(const swh_basin *b, const swcu_dims *d, const int *mask,
+              float *lu, float *luu, float *luh, float *lcu, float *lcv, float *llu, float *llv);
+int swh_metrics(const swh_basin *b, const swcu_dims *d,
+                float *dx, float *dy, float *dxt, float *dyt, float *dxh, float *dyh,
+                float *dxb, float *dyb, float *rlh_s);
+int swh_gaussian(const swcu_dims *d, const float *lu, double *ssh, double sigma, int nx0, int ny0);
+/* block_uniform_decomposition (core/decomposition.f90:427-503): interior start/size of block
+ * `i` of `nb` along an axis of `ncells` computational cells. */
+int swh_uniform_split(int ncells, int nb, int i, int *start, int *size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

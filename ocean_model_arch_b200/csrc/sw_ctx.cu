@@ -1,0 +1,626 @@
+// sw_ctx.cu -- Level B: the resident context (include/swcuda.h).  One block of the reference's
+// decomposition lives on one GPU; fields stay in HBM between steps (no per-step host round trip).
+//
+// Device layout: every field is a pitched 2-D array, pitch = width rounded up to 16 elements, so
+// each row starts on a 128-byte (fp64) / 64-byte (fp32) boundary; element (m,n) of the
+// reference's A(bnd_x1:bnd_x2, bnd_y1:bnd_y2) is at base[(n-bnd_y1)*pitch + (m-bnd_x1)].
+//
+// REFERENCE mode keeps all 32 real(8) + 17 real(4) arrays of ocean_type / grid_type and launches
+// the reference's kernel sequence (control/shallow_water/shallow_water.f90:22-94).
+// FUSED mode keeps the six prognostic arrays twice (ping-pong), hhq_rest, mu, six scratch arrays,
+// ten real(4) arrays and one mask byte per cell, and launches prep + update per step.
+//
+// Multi-GPU (y-slabs, one block per GPU): halo rows travel with ncclSend/ncclRecv on a side
+// stream; in FUSED mode the two boundary strips are computed first, their exchange overlaps the
+// interior update (replaces shared/mpp/sync.f90:294-374 + syncborder_block2D_gen_all.fi).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "sw_fused.h"
+
+using namespace swcu;
+
+namespace {
+
+// ---- NCCL through dlopen: libswcuda.so has no link-time NCCL dependency; single-GPU users never
+// load it, multi-GPU hosts get whatever libnccl.so.2 the process already holds (torch's) --------
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.h) return SWCU_OK;
+    const char *names[] = {getenv("SWCU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { set_error("cannot dlopen libnccl.so.2 (set SWCU_NCCL_LIB): %s", dlerror()); return SWCU_ERR_NCCL; }
+#define L(sym)                                                                        \
+    *(void **)(&g_nccl.sym) = dlsym(h, "nccl" #sym);                                  \
+    if (!g_nccl.sym) { set_error("libnccl lacks nccl" #sym); return SWCU_ERR_NCCL; }
+    L(GetUniqueId) L(CommInitRank) L(CommDestroy) L(GroupStart) L(GroupEnd) L(Send) L(Recv) L(GetErrorString)
+#undef L
+    g_nccl.h = h;
+    return SWCU_OK;
+}
+int nccl_fail(ncclResult_t r, const char *what)
+{
+    set_error("NCCL error %d (%s) in %s", (int)r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what);
+    return SWCU_ERR_NCCL;
+}
+#define SWCU_NCCL(call)                                        \
+    do {                                                       \
+        ncclResult_t r__ = (call);                             \
+        if (r__ != ncclSuccess) return nccl_fail(r__, #call);  \
+    } while (0)
+
+const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
+
+int mask_bit(int field)
+{
+    switch (field) {
+        case SWCU_F_LU: return MB_LU;
+        case SWCU_F_LCU: return MB_LCU;
+        case SWCU_F_LCV: return MB_LCV;
+        case SWCU_F_LUU: return MB_LUU;
+        case SWCU_F_LUH: return MB_LUH;
+        case SWCU_F_LLU: return MB_LLU;
+        case SWCU_F_LLV: return MB_LLV;
+        default: return 0;
+    }
+}
+
+}  // namespace
+
+struct swcu_ctx {
+    swcu_dims d;
+    swcu_params p;
+    int device = 0;
+    Geo g;
+    int pitch = 0, w = 0, h = 0;
+    size_t plane = 0;  // pitch * h elements
+    cudaStream_t st = nullptr, comm_st = nullptr;
+    cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, t0 = nullptr, t1 = nullptr;
+    double *f8[SWCU_NF8] = {};
+    float *f4[SWCU_NF4] = {};
+    double *alt[6] = {};  // FUSED: second copy of the prognostic arrays (ping-pong)
+    unsigned char *mask = nullptr;
+    bool alt_dirty = true;
+    bool has_rhs = false, has_rdiss = false;
+    int *bad_dev = nullptr;
+    int *bad_host = nullptr;  // pinned
+    long launches = 0;
+    long bytes = 0;
+    long steps_done = 0;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int dev_alloc(swcu_ctx *c, void **ptr, size_t bytes)
+{
+    SWCU_CUDA(cudaMalloc(ptr, bytes));
+    SWCU_CUDA(cudaMemsetAsync(*ptr, 0, bytes, c->st));
+    c->bytes += (long)bytes;
+    return SWCU_OK;
+}
+int alloc8(swcu_ctx *c, int f)
+{
+    if (c->f8[f]) return SWCU_OK;
+    return dev_alloc(c, (void **)&c->f8[f], c->plane * sizeof(double));
+}
+int alloc4(swcu_ctx *c, int f)
+{
+    if (c->f4[f - 100]) return SWCU_OK;
+    return dev_alloc(c, (void **)&c->f4[f - 100], c->plane * sizeof(float));
+}
+inline float *F4(swcu_ctx *c, int f) { return c->f4[f - 100]; }
+bool is_f8(int f) { return f >= 0 && f < SWCU_NF8; }
+bool is_f4(int f) { return f >= 100 && f < SWCU_F4_END; }
+bool is_tracer_field(int f) { return f >= SWCU_F_FLUX_X && f <= SWCU_F_FF1P; }
+
+struct Use { int dev; explicit Use(int d) { cudaGetDevice(&dev); if (dev != d) cudaSetDevice(d); else dev = -1; }
+             ~Use() { if (dev >= 0) cudaSetDevice(dev); } };
+
+// which real(8) fields the FUSED mode keeps resident
+bool fused_keeps8(const swcu_ctx *c, int f)
+{
+    switch (f) {
+        case SWCU_F_SSH: case SWCU_F_SSHP: case SWCU_F_UBRTR: case SWCU_F_UBRTRP: case SWCU_F_VBRTR: case SWCU_F_VBRTRP:
+        case SWCU_F_HHQ_REST: case SWCU_F_MU:
+        case SWCU_F_HHU: case SWCU_F_HHV: case SWCU_F_HHH: case SWCU_F_VORT: case SWCU_F_STR_T: case SWCU_F_STR_S:
+            return true;
+        case SWCU_F_RHSX: case SWCU_F_RHSY: return c->has_rhs;
+        default: return false;
+    }
+}
+bool fused_keeps4(const swcu_ctx *c, int f)
+{
+    if (f >= SWCU_F_DX && f <= SWCU_F_RLH_S) return true;
+    if (f == SWCU_F_R_DISS) return c->has_rdiss;
+    return false;
+}
+
+int state_slot(int f)
+{
+    for (int i = 0; i < 6; ++i) if (kState[i] == f) return i;
+    return -1;
+}
+
+// ---- halo rows over NCCL (y-slabs) ------------------------------------------------------------
+// Sends my first / last `nrows` interior rows to rank-1 / rank+1 and receives their rows into my
+// lower / upper halo rows.  Must be called between ncclGroupStart/End.
+template <typename T>
+int exchange_rows(swcu_ctx *c, T *base, int nrows, cudaStream_t st)
+{
+    const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+    const size_t cnt = (size_t)nrows * c->pitch;
+    const int lo = c->rank - 1, hi = c->rank + 1;
+    // row index (0-based in the array) of reference row n is n - bnd_y1
+    const long r_first = c->d.ny_start - c->d.bnd_y1, r_last = c->d.ny_end - c->d.bnd_y1;
+    if (lo >= 0) {
+        SWCU_NCCL(g_nccl.Send(base + (size_t)r_first * c->pitch, cnt, dt, lo, c->comm, st));
+        SWCU_NCCL(g_nccl.Recv(base + (size_t)(r_first - nrows) * c->pitch, cnt, dt, lo, c->comm, st));
+    }
+    if (hi < c->nranks) {
+        SWCU_NCCL(g_nccl.Send(base + (size_t)(r_last - nrows + 1) * c->pitch, cnt, dt, hi, c->comm, st));
+        SWCU_NCCL(g_nccl.Recv(base + (size_t)(r_last + 1) * c->pitch, cnt, dt, hi, c->comm, st));
+    }
+    return SWCU_OK;
+}
+
+// reference-mode halo sync of a list of real(8) fields: width 1, on the compute stream
+int sync_fields(swcu_ctx *c, std::initializer_list<int> fields)
+{
+    if (!c->comm) return SWCU_OK;
+    SWCU_NCCL(g_nccl.GroupStart());
+    for (int f : fields)
+        if (int rc = exchange_rows(c, c->f8[f], 1, c->st)) { g_nccl.GroupEnd(); return rc; }
+    SWCU_NCCL(g_nccl.GroupEnd());
+    return SWCU_OK;
+}
+
+#define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
+
+// control/shallow_water/shallow_water.f90:22-94 with the binders' argument choice
+// (interface/shallow_water/sw_interface.f90), then control/tracer.f90:44-61
+int step_reference(swcu_ctx *c, double tau)
+{
+    const Geo &g = c->g;
+    cudaStream_t st = c->st;
+    double **F = c->f8;
+    const swcu_params &p = c->p;
+    float *lu = F4(c, SWCU_F_LU), *luu = F4(c, SWCU_F_LUU), *luh = F4(c, SWCU_F_LUH), *lcu = F4(c, SWCU_F_LCU),
+          *lcv = F4(c, SWCU_F_LCV), *llu = F4(c, SWCU_F_LLU), *llv = F4(c, SWCU_F_LLV);
+    float *dx = F4(c, SWCU_F_DX), *dy = F4(c, SWCU_F_DY), *dxt = F4(c, SWCU_F_DXT), *dyt = F4(c, SWCU_F_DYT),
+          *dxh = F4(c, SWCU_F_DXH), *dyh = F4(c, SWCU_F_DYH), *dxb = F4(c, SWCU_F_DXB), *dyb = F4(c, SWCU_F_DYB);
+
+    RC(launch_sw_update_ssh(g, tau, lu, dx, dy, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_SSHN],
+                            F[SWCU_F_SSHP], F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], st));
+    c->launches++;
+    RC(sync_fields(c, {SWCU_F_SSHN}));
+    if (p.full_free_surface > 0) {
+        RC(launch_hh_update(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHQ_N],
+                            F[SWCU_F_HHU_N], F[SWCU_F_HHV_N], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_HHQ_REST], st));
+        c->launches++;
+        RC(sync_fields(c, {SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N}));
+    }
+    if (p.trans_terms > 0) {
+        RC(launch_uv_trans_vort(g, luu, dxt, dyt, dxb, dyb, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT], st));
+        RC(sync_fields(c, {SWCU_F_VORT}));
+        RC(launch_uv_trans(g, lcu, lcv, luu, dxh, dyh, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT],
+                           F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_HHH], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV], st));
+        c->launches += 2;
+        RC(sync_fields(c, {SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P}));
+    }
+    if (p.ksw_lat > 0) {
+        RC(launch_stress_components(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_UBRTRP],
+                                    F[SWCU_F_VBRTRP], F[SWCU_F_STR_T], F[SWCU_F_STR_S], st));
+        RC(sync_fields(c, {SWCU_F_STR_T, SWCU_F_STR_S}));
+        RC(launch_uv_diff2(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_MU], F[SWCU_F_STR_T],
+                           F[SWCU_F_STR_S], F[SWCU_F_HHQ], F[SWCU_F_HHH], F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st));
+        c->launches += 2;
+    }
+    RC(launch_sw_update_uv(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHU], F[SWCU_F_HHU_N],
+                           F[SWCU_F_HHU_P], F[SWCU_F_HHV], F[SWCU_F_HHV_N], F[SWCU_F_HHV_P], F[SWCU_F_HHH],
+                           F[SWCU_F_SSH], F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR],
+                           F[SWCU_F_VBRTRN], F[SWCU_F_VBRTRP], F4(c, SWCU_F_R_DISS), F4(c, SWCU_F_RLH_S),
+                           F[SWCU_F_RHSX], F[SWCU_F_RHSY], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV],
+                           F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st));
+    c->launches++;
+    RC(sync_fields(c, {SWCU_F_VBRTRN, SWCU_F_UBRTRN}));
+    RC(launch_sw_next_step(g, p.time_smooth, lu, lcu, lcv, F[SWCU_F_SSH], F[SWCU_F_SSHN], F[SWCU_F_SSHP],
+                           F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR], F[SWCU_F_VBRTRN],
+                           F[SWCU_F_VBRTRP], st));
+    c->launches++;
+    if (p.full_free_surface > 0) {
+        RC(launch_hh_shift(g, p.time_smooth, lu, llu, llv, luh, F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N],
+                           F[SWCU_F_HHU], F[SWCU_F_HHU_P], F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P],
+                           F[SWCU_F_HHV_N], F[SWCU_F_HHH], F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], st));
+        RC(launch_hh_init(g, p.full_free_surface, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                          F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
+                          F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
+                          F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], st));
+        c->launches += 2;
+        RC(sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH}));
+    }
+    RC(launch_check_ssh_err(g, lu, F[SWCU_F_SSH], c->bad_dev, st));
+    c->launches++;
+
+    if (p.use_tracers > 0) {
+        RC(launch_tran_diff_fluxes(g, lcu, lcv, dxt, dyt, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_FF1],
+                                   F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_MU], 1.0, F[SWCU_F_FLUX_X],
+                                   F[SWCU_F_FLUX_Y], st));
+        RC(sync_fields(c, {SWCU_F_FLUX_X, SWCU_F_FLUX_Y}));
+        RC(launch_tran_diff_tracer(g, lu, dx, dy, tau, F[SWCU_F_HHQ_N], F[SWCU_F_HHQ_P], F[SWCU_F_FLUX_X],
+                                   F[SWCU_F_FLUX_Y], F[SWCU_F_FF1P], F[SWCU_F_FF1N], st));
+        RC(sync_fields(c, {SWCU_F_FF1N}));
+        RC(launch_tracer_next_step(g, p.time_smooth, lu, F[SWCU_F_FF1N], F[SWCU_F_FF1P], F[SWCU_F_FF1], st));
+        c->launches += 3;
+    }
+    return SWCU_OK;
+}
+
+int step_fused(swcu_ctx *c, double tau)
+{
+    const Geo &g = c->g;
+    if (c->alt_dirty) {  // the frame / land cells of the write buffers must equal the read buffers
+        for (int i = 0; i < 6; ++i)
+            SWCU_CUDA(cudaMemcpyAsync(c->alt[i], c->f8[kState[i]], c->plane * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, c->st));
+        c->alt_dirty = false;
+    }
+    FusedArgs a;
+    a.ssh = c->f8[SWCU_F_SSH]; a.sshp = c->f8[SWCU_F_SSHP]; a.u = c->f8[SWCU_F_UBRTR]; a.up = c->f8[SWCU_F_UBRTRP];
+    a.v = c->f8[SWCU_F_VBRTR]; a.vp = c->f8[SWCU_F_VBRTRP];
+    a.ssh_o = c->alt[0]; a.sshp_o = c->alt[1]; a.u_o = c->alt[2]; a.up_o = c->alt[3]; a.v_o = c->alt[4]; a.vp_o = c->alt[5];
+    a.h_r = c->f8[SWCU_F_HHQ_REST]; a.mu = c->f8[SWCU_F_MU];
+    a.RHSx = c->has_rhs ? c->f8[SWCU_F_RHSX] : nullptr; a.RHSy = c->has_rhs ? c->f8[SWCU_F_RHSY] : nullptr;
+    a.hu = c->f8[SWCU_F_HHU]; a.hv = c->f8[SWCU_F_HHV]; a.hh = c->f8[SWCU_F_HHH];
+    a.vort = c->f8[SWCU_F_VORT]; a.str_t = c->f8[SWCU_F_STR_T]; a.str_s = c->f8[SWCU_F_STR_S];
+    a.dx = F4(c, SWCU_F_DX); a.dy = F4(c, SWCU_F_DY); a.dxt = F4(c, SWCU_F_DXT); a.dyt = F4(c, SWCU_F_DYT);
+    a.dxh = F4(c, SWCU_F_DXH); a.dyh = F4(c, SWCU_F_DYH); a.dxb = F4(c, SWCU_F_DXB); a.dyb = F4(c, SWCU_F_DYB);
+    a.rlh_s = F4(c, SWCU_F_RLH_S); a.rdis = c->has_rdiss ? F4(c, SWCU_F_R_DISS) : nullptr;
+    a.mask = c->mask; a.bad = c->bad_dev;
+    a.tau = tau; a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
+    a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;
+
+    const int ns = g.ny_start, ne = g.ny_end;
+    RC(launch_prep(g, a, ns - 1, ne + 1, c->st));
+    c->launches++;
+    if (!c->comm) {
+        RC(launch_update(g, a, ns, ne, c->st));
+        c->launches++;
+    } else {
+        // boundary strips (the two rows each neighbour needs) first, then the exchange on the side
+        // stream overlapped with the interior update
+        const bool lo = c->rank > 0, hi = c->rank + 1 < c->nranks;
+        int i0 = ns, i1 = ne;
+        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(launch_update(g, a, ns, e, c->st)); c->launches++; i0 = e + 1; }
+        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(launch_update(g, a, s, ne, c->st)); c->launches++; i1 = s - 1; }
+        SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->st));
+        SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
+        SWCU_NCCL(g_nccl.GroupStart());
+        for (int i = 0; i < 6; ++i)
+            if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
+        SWCU_NCCL(g_nccl.GroupEnd());
+        SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
+        if (i0 <= i1) { RC(launch_update(g, a, i0, i1, c->st)); c->launches++; }
+        SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
+    }
+    for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
+    return SWCU_OK;
+}
+
+template <typename T>
+int copy_in(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
+{
+    SWCU_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->pitch * sizeof(T), src, (size_t)c->w * sizeof(T),
+                                (size_t)c->w * sizeof(T), (size_t)c->h, kind, c->st));
+    return SWCU_OK;
+}
+template <typename T>
+int copy_out(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
+{
+    SWCU_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->w * sizeof(T), src, (size_t)c->pitch * sizeof(T),
+                                (size_t)c->w * sizeof(T), (size_t)c->h, kind, c->st));
+    return SWCU_OK;
+}
+
+int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
+{
+    if (!c || !src) { set_error("null argument"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    if (is_f8(field)) {
+        if (is_tracer_field(field) && !c->p.use_tracers) { set_error("tracer field without use_tracers"); return SWCU_ERR_STATE; }
+        if (fused && (field == SWCU_F_RHSX || field == SWCU_F_RHSY) && !c->has_rhs) {
+            c->has_rhs = true;  // the reference never assigns RHSx/RHSy; first upload makes them resident
+            RC(alloc8(c, SWCU_F_RHSX)); RC(alloc8(c, SWCU_F_RHSY));
+        }
+        if (fused && !fused_keeps8(c, field) && !is_tracer_field(field)) return SWCU_OK;  // derived: recomputed on device
+        RC(copy_in(c, c->f8[field], (const double *)src, kind));
+        if (fused && state_slot(field) >= 0) c->alt_dirty = true;
+        return SWCU_OK;
+    }
+    if (is_f4(field)) {
+        const int bit = mask_bit(field);
+        if (fused && bit) {
+            // stage through a scratch real(4) plane, then fold into the mask byte
+            float *tmp = nullptr;
+            SWCU_CUDA(cudaMalloc((void **)&tmp, c->plane * sizeof(float)));
+            SWCU_CUDA(cudaMemsetAsync(tmp, 0, c->plane * sizeof(float), c->st));
+            int rc = copy_in(c, tmp, (const float *)src, kind);
+            if (!rc) rc = launch_mask_set((long)c->plane, tmp, c->mask, bit, c->st);
+            cudaStreamSynchronize(c->st);
+            cudaFree(tmp);
+            return rc;
+        }
+        if (fused && field == SWCU_F_R_DISS && !c->has_rdiss) { c->has_rdiss = true; RC(alloc4(c, SWCU_F_R_DISS)); }
+        if (fused && !fused_keeps4(c, field)) return SWCU_OK;
+        return copy_in(c, F4(c, field), (const float *)src, kind);
+    }
+    set_error("unknown field id %d", field);
+    return SWCU_ERR_ARG;
+}
+
+int download_impl(swcu_ctx *c, int field, void *dst, bool to_device)
+{
+    if (!c || !dst) { set_error("null argument"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    int rc = SWCU_OK;
+    if (is_f8(field)) {
+        const double *src = c->f8[field];
+        if (fused) {
+            // after K8 the n+1 arrays equal the current ones on every cell they were written
+            if (field == SWCU_F_SSHN) src = c->f8[SWCU_F_SSH];
+            else if (field == SWCU_F_UBRTRN) src = c->f8[SWCU_F_UBRTR];
+            else if (field == SWCU_F_VBRTRN) src = c->f8[SWCU_F_VBRTR];
+            else if (!fused_keeps8(c, field) && !(is_tracer_field(field) && c->p.use_tracers)) {
+                set_error("field %d is not resident in FUSED mode", field);
+                return SWCU_ERR_STATE;
+            }
+        }
+        if (!src) { set_error("field %d not allocated", field); return SWCU_ERR_STATE; }
+        rc = copy_out(c, (double *)dst, src, kind);
+    } else if (is_f4(field)) {
+        const int bit = mask_bit(field);
+        if (fused && bit) {
+            float *tmp = nullptr;
+            SWCU_CUDA(cudaMalloc((void **)&tmp, c->plane * sizeof(float)));
+            rc = launch_mask_get((long)c->plane, tmp, c->mask, bit, c->st);
+            if (!rc) rc = copy_out(c, (float *)dst, tmp, kind);
+            cudaStreamSynchronize(c->st);
+            cudaFree(tmp);
+            return rc;
+        }
+        const float *src = F4(c, field);
+        if (!src) { set_error("field %d is not resident", field); return SWCU_ERR_STATE; }
+        rc = copy_out(c, (float *)dst, src, kind);
+    } else {
+        set_error("unknown field id %d", field);
+        return SWCU_ERR_ARG;
+    }
+    if (rc) return rc;
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    return SWCU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params, int device)
+{
+    if (!out || !params) { set_error("null argument"); return SWCU_ERR_ARG; }
+    RC(check_dims(dims));
+    if (params->mode != SWCU_MODE_REFERENCE && params->mode != SWCU_MODE_FUSED) { set_error("bad mode"); return SWCU_ERR_ARG; }
+    if (params->mode == SWCU_MODE_FUSED && params->use_tracers) {
+        set_error("tracers need SWCU_MODE_REFERENCE in this version");
+        return SWCU_ERR_STATE;
+    }
+    int ndev = 0;
+    SWCU_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("device %d of %d", device, ndev); return SWCU_ERR_ARG; }
+    Use use(device);
+    swcu_ctx *c = new swcu_ctx();
+    c->d = *dims; c->p = *params; c->device = device;
+    c->w = width(*dims); c->h = height(*dims);
+    c->pitch = (c->w + 15) / 16 * 16;
+    c->plane = (size_t)c->pitch * c->h;
+    c->g = make_geo(*dims, c->pitch);
+    int rc = SWCU_OK;
+#define TRY(call) do { if (!rc) rc = (call); } while (0)
+#define TRYCUDA(call) do { if (!rc) { cudaError_t e__ = (call); if (e__ != cudaSuccess) rc = cuda_fail(e__, #call); } } while (0)
+    TRYCUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->comm_st, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreate(&c->t0));
+    TRYCUDA(cudaEventCreate(&c->t1));
+    TRY(dev_alloc(c, (void **)&c->bad_dev, sizeof(int)));
+    TRYCUDA(cudaHostAlloc((void **)&c->bad_host, sizeof(int), cudaHostAllocDefault));
+    if (params->mode == SWCU_MODE_REFERENCE) {
+        for (int f = 0; f < SWCU_NF8; ++f) {
+            if (is_tracer_field(f) && !params->use_tracers) continue;
+            TRY(alloc8(c, f));
+        }
+        for (int f = 100; f < SWCU_F4_END; ++f) TRY(alloc4(c, f));
+    } else {
+        for (int f = 0; f < SWCU_NF8; ++f) if (fused_keeps8(c, f)) TRY(alloc8(c, f));
+        for (int i = 0; i < 6; ++i) TRY(dev_alloc(c, (void **)&c->alt[i], c->plane * sizeof(double)));
+        for (int f = 100; f < SWCU_F4_END; ++f) if (fused_keeps4(c, f)) TRY(alloc4(c, f));
+        TRY(dev_alloc(c, (void **)&c->mask, c->plane));
+    }
+    TRYCUDA(cudaStreamSynchronize(c->st));
+    if (rc) { swcu_destroy(c); return rc; }
+    *out = c;
+    return SWCU_OK;
+}
+
+int swcu_destroy(swcu_ctx *c)
+{
+    if (!c) return SWCU_OK;
+    Use use(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto &p : c->f8) cudaFree(p);
+    for (auto &p : c->f4) cudaFree(p);
+    for (auto &p : c->alt) cudaFree(p);
+    cudaFree(c->mask); cudaFree(c->bad_dev);
+    if (c->bad_host) cudaFreeHost(c->bad_host);
+    if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->comm_st) cudaStreamDestroy(c->comm_st);
+    delete c;
+    return SWCU_OK;
+}
+
+int swcu_upload(swcu_ctx *c, int field, const void *host) { return upload_impl(c, field, host, false); }
+int swcu_upload_from_device(swcu_ctx *c, int field, const void *dev) { return upload_impl(c, field, dev, true); }
+int swcu_download(swcu_ctx *c, int field, void *host) { return download_impl(c, field, host, false); }
+int swcu_download_to_device(swcu_ctx *c, int field, void *dev) { return download_impl(c, field, dev, true); }
+
+int swcu_envoke_hh_init(swcu_ctx *c)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    if (c->p.mode == SWCU_MODE_FUSED) return SWCU_OK;
+    Use use(c->device);
+    double **F = c->f8;
+    RC(launch_hh_init(c->g, c->p.full_free_surface, F4(c, SWCU_F_LU), F4(c, SWCU_F_LLU), F4(c, SWCU_F_LLV),
+                      F4(c, SWCU_F_LUH), F4(c, SWCU_F_DX), F4(c, SWCU_F_DY), F4(c, SWCU_F_DXT), F4(c, SWCU_F_DYT),
+                      F4(c, SWCU_F_DXH), F4(c, SWCU_F_DYH), F4(c, SWCU_F_DXB), F4(c, SWCU_F_DYB),
+                      F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
+                      F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
+                      F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], c->st));
+    c->launches++;
+    RC(sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH}));
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    return SWCU_OK;
+}
+
+int swcu_step(swcu_ctx *c, double tau, int nsteps)
+{
+    if (!c || nsteps < 0) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    for (int i = 0; i < nsteps; ++i) {
+        RC(c->p.mode == SWCU_MODE_FUSED ? step_fused(c, tau) : step_reference(c, tau));
+        c->steps_done++;
+    }
+    return SWCU_OK;
+}
+
+int swcu_synchronize(swcu_ctx *c, long *bad_cells)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    SWCU_CUDA(cudaMemcpyAsync(c->bad_host, c->bad_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SWCU_CUDA(cudaMemsetAsync(c->bad_dev, 0, sizeof(int), c->st));
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    SWCU_CUDA(cudaStreamSynchronize(c->comm_st));
+    const long bad = *c->bad_host;
+    if (bad_cells) *bad_cells = bad;
+    if (bad) { set_error("check_ssh_err: %ld sea cells with |ssh| >= 1e4 or NaN", bad); return SWCU_ERR_BLOWUP; }
+    return SWCU_OK;
+}
+
+int swcu_timer_start(swcu_ctx *c)
+{
+    if (!c) return SWCU_ERR_ARG;
+    Use use(c->device);
+    SWCU_CUDA(cudaEventRecord(c->t0, c->st));
+    return SWCU_OK;
+}
+int swcu_timer_stop(swcu_ctx *c, float *ms)
+{
+    if (!c || !ms) return SWCU_ERR_ARG;
+    Use use(c->device);
+    SWCU_CUDA(cudaEventRecord(c->t1, c->st));
+    SWCU_CUDA(cudaEventSynchronize(c->t1));
+    SWCU_CUDA(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return SWCU_OK;
+}
+long swcu_launch_count(const swcu_ctx *c) { return c ? c->launches : 0; }
+long swcu_device_bytes(const swcu_ctx *c) { return c ? c->bytes : 0; }
+void *swcu_stream(swcu_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+int swcu_comm_unique_id(void *id128)
+{
+    if (!id128) return SWCU_ERR_ARG;
+    RC(nccl_load());
+    ncclUniqueId id;
+    SWCU_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return SWCU_OK;
+}
+
+int swcu_comm_init(swcu_ctx *c, int nranks, int rank, const void *id128)
+{
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    if (c->comm) { set_error("communicator already attached"); return SWCU_ERR_STATE; }
+    if (nranks == 1) return SWCU_OK;
+    RC(nccl_load());
+    Use use(c->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    SWCU_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->nranks = nranks; c->rank = rank;
+    return SWCU_OK;
+}
+
+int swcu_comm_destroy(swcu_ctx *c)
+{
+    if (!c || !c->comm) return SWCU_OK;
+    Use use(c->device);
+    cudaDeviceSynchronize();
+    SWCU_NCCL(g_nccl.CommDestroy(c->comm));
+    c->comm = nullptr; c->nranks = 1; c->rank = 0;
+    return SWCU_OK;
+}
+
+int swcu_halo_exchange(swcu_ctx *c, int field)
+{
+    if (!c) return SWCU_ERR_ARG;
+    if (!c->comm) return SWCU_OK;
+    Use use(c->device);
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    SWCU_NCCL(g_nccl.GroupStart());
+    int rc = SWCU_OK;
+    if (is_f8(field) && c->f8[field]) {
+        rc = exchange_rows(c, c->f8[field], fused ? 2 : 1, c->st);
+        if (fused && state_slot(field) >= 0) c->alt_dirty = true;
+    } else if (is_f4(field) && F4(c, field)) rc = exchange_rows(c, F4(c, field), fused ? 2 : 1, c->st);
+    else { set_error("field %d is not resident", field); rc = SWCU_ERR_STATE; }
+    ncclResult_t r = g_nccl.GroupEnd();
+    if (rc) return rc;
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    return SWCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// sw_kernels_ref.cu -- Level A: one CUDA kernel per reference kernel (K1..K11 + 3 tracer kernels),
+// written for sm_100a.  One thread per cell, warps run along the contiguous m (x) dimension so
+// every global access is coalesced; masked cells are handled with predicated stores (the value is
+// always computed, `if (mask>0.5)` guards only the store, exactly like the reference keeps the old
+// value).  The arithmetic lives in sw_formulas.cuh.  Compile with -fmad=false.
+#include "sw_common.h"
+
+namespace swcu {
+
+namespace {
+
+constexpr int BX = 64;  // threads along m (2 warps = 512 contiguous bytes of fp64 per row)
+constexpr int BY = 4;   // rows per CTA
+
+inline dim3 grid_for(int m0, int m1, int n0, int n1)
+{
+    return dim3((unsigned)((m1 - m0 + BX) / BX), (unsigned)((n1 - n0 + BY) / BY), 1);
+}
+inline int launched(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
+}
+
+#define SWCU_CELL(m0, n0, m1, n1)                          \
+    const int m = (m0) + blockIdx.x * BX + threadIdx.x;    \
+    const int n = (n0) + blockIdx.y * BY + threadIdx.y;    \
+    if (m > (m1) || n > (n1)) return;                      \
+    const long c = ix(g, m, n);                            \
+    const int p = g.pitch;                                 \
+    (void)p
+
+// K1 -- kernel/shallow_water/vel_ssh.f90:94-104
+__global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, double tau,
+        const float *__restrict__ lu, const float *__restrict__ dx, const float *__restrict__ dy,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const double *__restrict__ hhu, const double *__restrict__ hhv, double *__restrict__ sshn,
+        const double *__restrict__ sshp, const double *__restrict__ u, const double *__restrict__ v)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lu[c])) sshn[c] = f_sshn(c, p, tau, dx, dy, dxh, dyh, hhu, hhv, sshp, u, v);
+}
+
+// K7 -- kernel/shallow_water/vel_ssh.f90:163-193
+__global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, double tau,
+        const float *__restrict__ lcu, const float *__restrict__ lcv,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        const double *__restrict__ hhu, const double *__restrict__ hhun, const double *__restrict__ hhup,
+        const double *__restrict__ hhv, const double *__restrict__ hhvn, const double *__restrict__ hhvp,
+        const double *__restrict__ hhh, const double *__restrict__ ssh,
+        const double *__restrict__ u, double *__restrict__ un, const double *__restrict__ up,
+        const double *__restrict__ v, double *__restrict__ vn, const double *__restrict__ vp,
+        const float *__restrict__ rdis, const float *__restrict__ rlh_s,
+        const double *__restrict__ RHSx, const double *__restrict__ RHSy,
+        const double *__restrict__ RHSx_adv, const double *__restrict__ RHSy_adv,
+        const double *__restrict__ RHSx_dif, const double *__restrict__ RHSy_dif)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lcu[c]))
+        un[c] = f_un(c, p, tau, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
+                     rdis[c] + rdis[c + 1], dxt, dyh, dxb, dyb, rlh_s, hhh, ssh, v, up);
+    if (on(lcv[c]))
+        vn[c] = f_vn(c, p, tau, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
+                     rdis[c] + rdis[c + p], dyt, dxh, dxb, dyb, rlh_s, hhh, ssh, u, vp);
+}
+
+// K8 -- kernel/shallow_water/vel_ssh.f90:226-243 (range grown by one cell)
+__global__ void __launch_bounds__(BX *BY) k_sw_next_step(Geo g, double ts,
+        const float *__restrict__ lu, const float *__restrict__ lcu, const float *__restrict__ lcv,
+        double *__restrict__ ssh, const double *__restrict__ sshn, double *__restrict__ sshp,
+        double *__restrict__ u, const double *__restrict__ un, double *__restrict__ up,
+        double *__restrict__ v, const double *__restrict__ vn, double *__restrict__ vp)
+{
+    SWCU_CELL(g.nx_start - 1, g.ny_start - 1, g.nx_end + 1, g.ny_end + 1);
+    if (on(lu[c])) {
+        sshp[c] = f_filter(ssh[c], sshn[c], sshp[c], ts);
+        ssh[c] = sshn[c];
+    }
+    if (on(lcu[c])) {
+        up[c] = f_filter(u[c], un[c], up[c], ts);
+        u[c] = un[c];
+    }
+    if (on(lcv[c])) {
+        vp[c] = f_filter(v[c], vn[c], vp[c], ts);
+        v[c] = vn[c];
+    }
+}
+
+// K3 -- kernel/shallow_water/vel_ssh.f90:269-279
+__global__ void __launch_bounds__(BX *BY) k_uv_trans_vort(Geo g, const float *__restrict__ luu,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ vort)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(luu[c])) vort[c] = f_vort(c, p, dxt, dyt, dxb, dyb, u, v);
+}
+
+// K4 -- kernel/shallow_water/vel_ssh.f90:318-371
+__global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g,
+        const float *__restrict__ lcu, const float *__restrict__ lcv, const float *__restrict__ luu,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ vort,
+        const double *__restrict__ hu, const double *__restrict__ hv, const double *__restrict__ hh,
+        double *__restrict__ RHSx, double *__restrict__ RHSy)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, p, luu[c], luu[c - p], dxh, dyh, u, v, vort, hu, hv, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, p, dxh, dyh, u, v, vort, hu, hv, hh);
+}
+
+// K6 -- kernel/shallow_water/vel_ssh.f90:414-450
+__global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g,
+        const float *__restrict__ lcu, const float *__restrict__ lcv,
+        const float *__restrict__ dx, const float *__restrict__ dy,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        const double *__restrict__ mu, const double *__restrict__ str_t, const double *__restrict__ str_s,
+        const double *__restrict__ hq, const double *__restrict__ hh,
+        double *__restrict__ RHSx, double *__restrict__ RHSy)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, p, hq[c], hq[c + 1], dy, dxt, dyh, dxb, mu, str_t, str_s, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, p, hq[c], hq[c + p], dx, dyt, dxh, dyb, mu, str_t, str_s, hh);
+}
+
+// K5 -- kernel/shallow_water/mixing.f90:38-56
+__global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g,
+        const float *__restrict__ lu, const float *__restrict__ luu,
+        const float *__restrict__ dx, const float *__restrict__ dy,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        const double *__restrict__ u, const double *__restrict__ v,
+        double *__restrict__ str_t, double *__restrict__ str_s)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lu[c])) str_t[c] = f_str_t(c, p, dx, dy, dxh, dyh, u, v);
+    if (on(luu[c])) str_s[c] = f_str_s(c, p, dxt, dyt, dxb, dyb, u, v);
+}
+
+// the three interpolations of hh_init / hh_update for one source depth (depth.f90:57-94);
+// the T-point depth of the neighbours is re-evaluated in registers (same expression as the
+// whole-array statement) so the kernel needs no grid-wide ordering.
+struct Interp3 { double hu, hv, hh; };
+__device__ __forceinline__ Interp3 interp3(double q_c, double q_e, double q_n, double q_en, long c, int p,
+        const float *__restrict__ lu, const float *__restrict__ dx, const float *__restrict__ dy,
+        float dxt, float dyt, float dxh, float dyh, float dxb, float dyb)
+{
+    const long e = c + 1, no = c + p, en = c + 1 + p;
+    Interp3 r;
+    r.hu = f_interp2(q_c, q_e, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e], dxt, dyh);
+    r.hv = f_interp2(q_c, q_n, dx[c], dy[c], lu[c], dx[no], dy[no], lu[no], dxh, dyt);
+    r.hh = f_interp4(q_c, q_e, q_n, q_en, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e],
+                     dx[no], dy[no], lu[no], dx[en], dy[en], lu[en], dxb, dyb);
+    return r;
+}
+
+// K10 -- kernel/shallow_water/depth.f90:48-97
+__global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, double ffs,
+        const float *__restrict__ lu, const float *__restrict__ llu, const float *__restrict__ llv,
+        const float *__restrict__ luh,
+        const float *__restrict__ dx, const float *__restrict__ dy,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        double *__restrict__ hq, double *__restrict__ hqp, double *__restrict__ hqn,
+        double *__restrict__ hu, double *__restrict__ hup, double *__restrict__ hun,
+        double *__restrict__ hv, double *__restrict__ hvp, double *__restrict__ hvn,
+        double *__restrict__ hh, double *__restrict__ hhp, double *__restrict__ hhn,
+        const double *__restrict__ sh, const double *__restrict__ shp, const double *__restrict__ h_r)
+{
+    SWCU_CELL(g.bx1, g.by1, g.bx2, g.by2);
+    const double q = h_r[c] + sh[c] * ffs, qp = h_r[c] + shp[c] * ffs, qn = h_r[c];
+    hq[c] = q; hqp[c] = qp; hqn[c] = qn;  // whole-array statements, depth.f90:48-50
+    if (m < g.nx_start - 1 || m > g.nx_end || n < g.ny_start - 1 || n > g.ny_end) return;
+    const long e = c + 1, no = c + p, en = c + 1 + p;
+    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
+    if (!(wu || wv || wh)) return;
+    const float a = dxt[c], b = dyt[c], cc = dxh[c], d = dyh[c], ee = dxb[c], f = dyb[c];
+    const Interp3 r = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs,
+                              c, p, lu, dx, dy, a, b, cc, d, ee, f);
+    const Interp3 rp = interp3(qp, h_r[e] + shp[e] * ffs, h_r[no] + shp[no] * ffs, h_r[en] + shp[en] * ffs,
+                               c, p, lu, dx, dy, a, b, cc, d, ee, f);
+    const Interp3 rn = interp3(qn, h_r[e], h_r[no], h_r[en], c, p, lu, dx, dy, a, b, cc, d, ee, f);
+    if (wu) { hu[c] = r.hu; hup[c] = rp.hu; hun[c] = rn.hu; }
+    if (wv) { hv[c] = r.hv; hvp[c] = rp.hv; hvn[c] = rn.hv; }
+    if (wh) { hh[c] = r.hh; hhp[c] = rp.hh; hhn[c] = rn.hh; }
+}
+
+// K2 -- kernel/shallow_water/depth.f90:129-160
+__global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g,
+        const float *__restrict__ lu, const float *__restrict__ llu, const float *__restrict__ llv,
+        const float *__restrict__ luh,
+        const float *__restrict__ dx, const float *__restrict__ dy,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const float *__restrict__ dxb, const float *__restrict__ dyb,
+        double *__restrict__ hqn, double *__restrict__ hun, double *__restrict__ hvn, double *__restrict__ hhn,
+        const double *__restrict__ sh, const double *__restrict__ h_r)
+{
+    SWCU_CELL(g.bx1, g.by1, g.bx2, g.by2);
+    const double qn = h_r[c] + sh[c];
+    hqn[c] = qn;  // depth.f90:129
+    if (m < g.nx_start - 1 || m > g.nx_end || n < g.ny_start - 1 || n > g.ny_end) return;
+    const long e = c + 1, no = c + p, en = c + 1 + p;
+    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
+    if (!(wu || wv || wh)) return;
+    const Interp3 rn = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, p, lu, dx, dy,
+                               dxt[c], dyt[c], dxh[c], dyh[c], dxb[c], dyb[c]);
+    if (wu) hun[c] = rn.hu;
+    if (wv) hvn[c] = rn.hv;
+    if (wh) hhn[c] = rn.hh;
+}
+
+// K9 -- kernel/shallow_water/depth.f90:185-209
+__global__ void __launch_bounds__(BX *BY) k_hh_shift(Geo g, double ts,
+        const float *__restrict__ lu, const float *__restrict__ llu, const float *__restrict__ llv,
+        const float *__restrict__ luh,
+        double *__restrict__ hq, double *__restrict__ hqp, const double *__restrict__ hqn,
+        double *__restrict__ hu, double *__restrict__ hup, const double *__restrict__ hun,
+        double *__restrict__ hv, double *__restrict__ hvp, const double *__restrict__ hvn,
+        double *__restrict__ hh, double *__restrict__ hhp, const double *__restrict__ hhn)
+{
+    SWCU_CELL(g.nx_start - 1, g.ny_start - 1, g.nx_end + 1, g.ny_end + 1);
+    if (on(llu[c])) { hup[c] = f_filter(hu[c], hun[c], hup[c], ts); hu[c] = hun[c]; }
+    if (on(llv[c])) { hvp[c] = f_filter(hv[c], hvn[c], hvp[c], ts); hv[c] = hvn[c]; }
+    if (on(lu[c]))  { hqp[c] = f_filter(hq[c], hqn[c], hqp[c], ts); hq[c] = hqn[c]; }
+    if (on(luh[c])) { hhp[c] = f_filter(hh[c], hhn[c], hhp[c], ts); hh[c] = hhn[c]; }
+}
+
+// K11 -- kernel/shallow_water/vel_ssh.f90:52-66
+__global__ void __launch_bounds__(BX *BY) k_check_ssh_err(Geo g, const float *__restrict__ lu,
+        const double *__restrict__ ssh, int *__restrict__ bad)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lu[c])) {
+        const double s = ssh[c];
+        if (!(s < 10000.0 && s > -10000.0)) atomicAdd(bad, 1);
+    }
+}
+
+// kernel/tracer/leapfrog_tracer.f90:55-96
+__global__ void __launch_bounds__(BX *BY) k_tran_diff_fluxes(Geo g,
+        const float *__restrict__ lcu, const float *__restrict__ lcv,
+        const float *__restrict__ dxt, const float *__restrict__ dyt,
+        const float *__restrict__ dxh, const float *__restrict__ dyh,
+        const double *__restrict__ hhu, const double *__restrict__ hhv, const double *__restrict__ ff,
+        const double *__restrict__ uu, const double *__restrict__ vv, const double *__restrict__ mu,
+        double factor_mu, double *__restrict__ flux_x, double *__restrict__ flux_y)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    const long e = c + 1, no = c + p;
+    if (on(lcu[c])) {
+        const double dfdx = ff[e] - ff[c];
+        const double mu_1d = (mu[c] + mu[e]) / 2.0 * factor_mu * dyh[c] / dxt[c];
+        const double flux_diff = mu_1d * hhu[c] * dfdx;
+        const double flux_adv = -uu[c] * hhu[c] * dyh[c] * (ff[c] + ff[e]) / 2.0;
+        flux_x[c] = flux_adv + flux_diff + 0.0;
+    }
+    if (on(lcv[c])) {
+        const double dfdy = ff[no] - ff[c];
+        const double mu_1d = (mu[c] + mu[no]) / 2.0 * factor_mu * dxh[c] / dyt[c];
+        const double flux_diff = mu_1d * hhv[c] * dfdy;
+        const double flux_adv = -vv[c] * hhv[c] * dxh[c] * (ff[c] + ff[no]) / 2.0;
+        flux_y[c] = flux_adv + flux_diff + 0.0;
+    }
+}
+
+// kernel/tracer/leapfrog_tracer.f90:125-139
+__global__ void __launch_bounds__(BX *BY) k_tran_diff_tracer(Geo g, const float *__restrict__ lu,
+        const float *__restrict__ dx, const float *__restrict__ dy, double tau,
+        const double *__restrict__ hhqn, const double *__restrict__ hhqp,
+        const double *__restrict__ flux_x, const double *__restrict__ flux_y,
+        const double *__restrict__ ffp, double *__restrict__ ffn)
+{
+    SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    if (on(lu[c])) {
+        const double bp = hhqn[c] * dx[c] * dy[c] / tau / 2.0;
+        const double bp0 = hhqp[c] * dx[c] * dy[c] / tau / 2.0;
+        const double rhs = flux_x[c] - flux_x[c - 1] + flux_y[c] - flux_y[c - p];
+        const double eta = bp0 * ffp[c] + rhs;
+        ffn[c] = eta / bp;
+    }
+}
+
+// kernel/tracer/leapfrog_tracer.f90:159-168
+__global__ void __launch_bounds__(BX *BY) k_tracer_next_step(Geo g, double ts, const float *__restrict__ lu,
+        const double *__restrict__ ffn, double *__restrict__ ffp, double *__restrict__ ff)
+{
+    SWCU_CELL(g.nx_start - 1, g.ny_start - 1, g.nx_end + 1, g.ny_end + 1);
+    if (on(lu[c])) {
+        ffp[c] = f_filter(ff[c], ffn[c], ffp[c], ts);
+        ff[c] = ffn[c];
+    }
+}
+
+const dim3 kBlock(BX, BY, 1);
+
+}  // namespace
+
+#define GRID_S grid_for(g.nx_start, g.nx_end, g.ny_start, g.ny_end)
+#define GRID_SP grid_for(g.nx_start - 1, g.nx_end + 1, g.ny_start - 1, g.ny_end + 1)
+#define GRID_ALL grid_for(g.bx1, g.bx2, g.by1, g.by2)
+
+int launch_sw_update_ssh(const Geo &g, double tau, const float *lu, const float *dx, const float *dy,
+        const float *dxh, const float *dyh, const double *hhu, const double *hhv, double *sshn,
+        const double *sshp, const double *u, const double *v, cudaStream_t st)
+{
+    k_sw_update_ssh<<<GRID_S, kBlock, 0, st>>>(g, tau, lu, dx, dy, dxh, dyh, hhu, hhv, sshn, sshp, u, v);
+    return launched("sw_update_ssh");
+}
+
+int launch_sw_update_uv(const Geo &g, double tau, const float *lcu, const float *lcv,
+        const float *dxt, const float *dyt, const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        const double *hhu, const double *hhun, const double *hhup,
+        const double *hhv, const double *hhvn, const double *hhvp, const double *hhh, const double *ssh,
+        const double *u, double *un, const double *up, const double *v, double *vn, const double *vp,
+        const float *rdis, const float *rlh_s, const double *RHSx, const double *RHSy,
+        const double *RHSx_adv, const double *RHSy_adv, const double *RHSx_dif, const double *RHSy_dif,
+        cudaStream_t st)
+{
+    k_sw_update_uv<<<GRID_S, kBlock, 0, st>>>(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb,
+            hhu, hhun, hhup, hhv, hhvn, hhvp, hhh, ssh, u, un, up, v, vn, vp, rdis, rlh_s,
+            RHSx, RHSy, RHSx_adv, RHSy_adv, RHSx_dif, RHSy_dif);
+    return launched("sw_update_uv");
+}
+
+int launch_sw_next_step(const Geo &g, double ts, const float *lu, const float *lcu, const float *lcv,
+        double *ssh, double *sshn, double *sshp, double *u, double *un, double *up,
+        double *v, double *vn, double *vp, cudaStream_t st)
+{
+    k_sw_next_step<<<GRID_SP, kBlock, 0, st>>>(g, ts, lu, lcu, lcv, ssh, sshn, sshp, u, un, up, v, vn, vp);
+    return launched("sw_next_step");
+}
+
+int launch_uv_trans_vort(const Geo &g, const float *luu, const float *dxt, const float *dyt,
+        const float *dxb, const float *dyb, const double *u, const double *v, double *vort, cudaStream_t st)
+{
+    k_uv_trans_vort<<<GRID_S, kBlock, 0, st>>>(g, luu, dxt, dyt, dxb, dyb, u, v, vort);
+    return launched("uv_trans_vort");
+}
+
+int launch_uv_trans(const Geo &g, const float *lcu, const float *lcv, const float *luu,
+        const float *dxh, const float *dyh, const double *u, const double *v, const double *vort,
+        const double *hu, const double *hv, const double *hh, double *RHSx, double *RHSy, cudaStream_t st)
+{
+    k_uv_trans<<<GRID_S, kBlock, 0, st>>>(g, lcu, lcv, luu, dxh, dyh, u, v, vort, hu, hv, hh, RHSx, RHSy);
+    return launched("uv_trans");
+}
+
+int launch_uv_diff2(const Geo &g, const float *lcu, const float *lcv,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        const double *mu, const double *str_t, const double *str_s, const double *hq, const double *hh,
+        double *RHSx, double *RHSy, cudaStream_t st)
+{
+    k_uv_diff2<<<GRID_S, kBlock, 0, st>>>(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                                          mu, str_t, str_s, hq, hh, RHSx, RHSy);
+    return launched("uv_diff2");
+}
+
+int launch_stress_components(const Geo &g, const float *lu, const float *luu,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        const double *u, const double *v, double *str_t, double *str_s, cudaStream_t st)
+{
+    k_stress_components<<<GRID_S, kBlock, 0, st>>>(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                                                   u, v, str_t, str_s);
+    return launched("stress_components");
+}
+
+int launch_hh_init(const Geo &g, int ffs, const float *lu, const float *llu, const float *llv, const float *luh,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
+        double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn,
+        const double *sh, const double *shp, const double *h_r, cudaStream_t st)
+{
+    k_hh_init<<<GRID_ALL, kBlock, 0, st>>>(g, (double)ffs, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+            hq, hqp, hqn, hu, hup, hun, hv, hvp, hvn, hh, hhp, hhn, sh, shp, h_r);
+    return launched("hh_init");
+}
+
+int launch_hh_update(const Geo &g, const float *lu, const float *llu, const float *llv, const float *luh,
+        const float *dx, const float *dy, const float *dxt, const float *dyt,
+        const float *dxh, const float *dyh, const float *dxb, const float *dyb,
+        double *hqn, double *hun, double *hvn, double *hhn, const double *sh, const double *h_r, cudaStream_t st)
+{
+    k_hh_update<<<GRID_ALL, kBlock, 0, st>>>(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                                             hqn, hun, hvn, hhn, sh, h_r);
+    return launched("hh_update");
+}
+
+int launch_hh_shift(const Geo &g, double ts, const float *lu, const float *llu, const float *llv, const float *luh,
+        double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
+        double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn, cudaStream_t st)
+{
+    k_hh_shift<<<GRID_SP, kBlock, 0, st>>>(g, ts, lu, llu, llv, luh, hq, hqp, hqn, hu, hup, hun,
+                                           hv, hvp, hvn, hh, hhp, hhn);
+    return launched("hh_shift");
+}
+
+int launch_check_ssh_err(const Geo &g, const float *lu, const double *ssh, int *bad, cudaStream_t st)
+{
+    k_check_ssh_err<<<GRID_S, kBlock, 0, st>>>(g, lu, ssh, bad);
+    return launched("check_ssh_err");
+}
+
+int launch_tran_diff_fluxes(const Geo &g, const float *lcu, const float *lcv,
+        const float *dxt, const float *dyt, const float *dxh, const float *dyh,
+        const double *hhu, const double *hhv, const double *ff, const double *uu, const double *vv,
+        const double *mu, double factor_mu, double *flux_x, double *flux_y, cudaStream_t st)
+{
+    k_tran_diff_fluxes<<<GRID_S, kBlock, 0, st>>>(g, lcu, lcv, dxt, dyt, dxh, dyh, hhu, hhv, ff, uu, vv, mu,
+                                                  factor_mu, flux_x, flux_y);
+    return launched("tran_diff_fluxes");
+}
+
+int launch_tran_diff_tracer(const Geo &g, const float *lu, const float *dx, const float *dy, double tau,
+        const double *hhqn, const double *hhqp, const double *flux_x, const double *flux_y,
+        const double *ffp, double *ffn, cudaStream_t st)
+{
+    k_tran_diff_tracer<<<GRID_S, kBlock, 0, st>>>(g, lu, dx, dy, tau, hhqn, hhqp, flux_x, flux_y, ffp, ffn);
+    return launched("tran_diff_tracer");
+}
+
+int launch_tracer_next_step(const Geo &g, double ts, const float *lu, const double *ffn, double *ffp, double *ff,
+        cudaStream_t st)
+{
+    k_tracer_next_step<<<GRID_SP, kBlock, 0, st>>>(g, ts, lu, ffn, ffp, ff);
+    return launched("tracer_next_step");
+}
+
+}  // namespace swcu

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's algorithm layer for the shallow-water path.
+
+Names follow the reference: the four .par files (configs/*.f90), `domain` geometry
+(core/decomposition.f90), `init_grid_data` / `init_ocean_data` (control/init_data.f90) and
+`expl_shallow_water(tau)` (control/shallow_water/shallow_water.f90:22).  All numerics happen in
+libswcuda.so (CUDA kernels; C++ host init); this file only moves arrays and calls the C ABI.
+"""
+import ctypes as C
+import dataclasses
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import FIELD_ID, F4_NAMES, F8_NAMES, MODE_FUSED, MODE_REFERENCE, SwcuDims, SwcuParams, SwhBasin, check
+
+
+# ----------------------------------------------------------------------------- configs (.par)
+def read_par(path):
+    """legacy/service/read_write_parameters.f90:7-42 (readpar): one value per line, text after the
+    first ':' is a comment."""
+    vals = []
+    with open(path) as f:
+        for line in f:
+            if not line.strip():
+                continue
+            vals.append(line.split(":", 1)[0].strip())
+    return vals
+
+
+def _f(s):
+    return float(s.lower().replace("d", "e"))
+
+
+@dataclasses.dataclass
+class BasinPar:  # configs/basinpar.f90:64-83 ; defaults = shipped basin.par
+    nx: int = 1525
+    ny: int = 1115
+    dxst: float = 0.00312
+    dyst: float = 0.00225
+    rlon: float = 34.751560
+    rlat: float = 44.801125
+    curve_grid: int = 1
+    rotation_on_lon: float = 0.0
+    rotation_on_lat: float = 0.0
+    mask_file_name: str = "none"
+    bottom_topography_file_name: str = "none"
+
+    @classmethod
+    def from_file(cls, path):
+        v = read_par(path)
+        if int(v[9]) != 0 or int(v[10]) != 0:
+            raise ValueError("only regular grids (xgr_type = ygr_type = 0) are supported")
+        return cls(nx=int(v[0]), ny=int(v[1]), dxst=_f(v[5]), dyst=_f(v[6]), rlon=_f(v[7]), rlat=_f(v[8]),
+                   curve_grid=int(v[11]), rotation_on_lon=_f(v[12]), rotation_on_lat=_f(v[13]),
+                   mask_file_name=v[18].split()[0], bottom_topography_file_name=v[19].split()[0])
+
+    def basin(self):
+        return SwhBasin(self.nx, self.ny, self.dxst, self.dyst, self.rlon, self.rlat, self.curve_grid,
+                        self.rotation_on_lon, self.rotation_on_lat)
+
+
+@dataclasses.dataclass
+class SwPar:  # configs/sw.f90:34-41 ; defaults = shipped sw.par
+    full_free_surface: int = 1
+    trans_terms: int = 1
+    ksw_lat: int = 1
+    time_smooth: float = 0.5
+    lvisc_2: float = 1.0e3
+    use_tracers: int = 0
+    tracer_num: int = 1
+    ssh_init_file_name: str = "none"
+
+    @classmethod
+    def from_file(cls, path):
+        v = read_par(path)
+        return cls(int(v[0]), int(v[1]), int(v[2]), _f(v[3]), _f(v[4]), int(v[5]), int(v[6]), v[7].split()[0])
+
+
+@dataclasses.dataclass
+class ParallelPar:  # configs/parallel.f90:34-42
+    mod_decomposition: int = 0
+    bppnx: int = 1
+    bppny: int = 1
+
+    @classmethod
+    def from_file(cls, path):
+        v = read_par(path)
+        return cls(int(v[0]), int(v[2]), int(v[3]))
+
+
+@dataclasses.dataclass
+class RunPar:  # tools/time_manager.f90:139-175 ; time_step and run_duration are real(4) there
+    time_step: float = 1.0
+    run_duration: float = 0.007
+
+    @classmethod
+    def from_file(cls, path):
+        v = read_par(path)
+        return cls(_f(v[1]), _f(v[2]))
+
+    @property
+    def tau(self):
+        return float(np.float32(self.time_step))  # tools/time_manager.f90:270
+
+    @property
+    def num_step_max(self):
+        nstep_per_day = np.rint(np.float32(86400.0) / np.float32(self.time_step))  # :226
+        return int(np.float32(self.run_duration) * np.float32(nstep_per_day))       # :266
+
+
+def read_mask_file(path, nx, ny):
+    """tools/io.f90:61-71: a comment line, then ny rows of nx digits, first row = n = ny."""
+    with open(path) as f:
+        f.readline()
+        rows = [f.readline().rstrip("\n") for _ in range(ny)]
+    m = np.empty((ny, nx), dtype=np.int32)
+    for i, row in enumerate(rows):
+        if len(row) < nx:
+            raise ValueError("mask row too short")
+        m[ny - 1 - i, :] = np.frombuffer(row[:nx].encode(), dtype=np.uint8) - ord("0")
+    return m
+
+
+# ----------------------------------------------------------------------------- decomposition
+def block_dims(nx, ny, bnx, bny, bm, bn):
+    """block_uniform_decomposition (core/decomposition.f90:427-503) for block (bm, bn), 0-based."""
+    L = _lib.lib()
+    xs, xn, ys, yn = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(L.swh_uniform_split(nx - 4, bnx, bm, C.byref(xs), C.byref(xn)))
+    check(L.swh_uniform_split(ny - 4, bny, bn, C.byref(ys), C.byref(yn)))
+    x0, y0 = 3 + xs.value, 3 + ys.value
+    return SwcuDims(x0, x0 + xn.value - 1, y0, y0 + yn.value - 1,
+                    x0 - 2, x0 + xn.value + 1, y0 - 2, y0 + yn.value + 1)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- host inputs
+class BlockInputs:
+    """What init_grid_data + init_ocean_data leave in grid_data / ocean_data for one block
+    (control/init_data.f90:29-125), as host arrays in the reference layout."""
+
+    def __init__(self, basin: BasinPar, sw: SwPar, dims: SwcuDims, mask=None, *, hhq_rest=100.0,
+                 keep_mu=False, r_diss=0.0):
+        L = _lib.lib()
+        self.dims = dims
+        shape = dims.shape
+        b = basin.basin()
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.int32)
+            assert mask.shape == (basin.ny, basin.nx)
+        self.f = {}
+        for n in F4_NAMES:
+            self.f[n] = np.zeros(shape, dtype=np.float32)
+        f = self.f
+        check(L.swh_masks(C.byref(b), C.byref(dims), _ptr(mask) if mask is not None else None,
+                          *[_ptr(f[n]) for n in ("lu", "luu", "luh", "lcu", "lcv", "llu", "llv")]))
+        check(L.swh_metrics(C.byref(b), C.byref(dims),
+                            *[_ptr(f[n]) for n in ("dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb", "rlh_s")]))
+        if r_diss:
+            f["r_diss"][:] = np.float32(r_diss)
+        f["hhq_rest"] = np.full(shape, float(hhq_rest), dtype=np.float64)   # init_data.f90:112-114
+        # Gaussian bump on the sea cells of the global interior that this block's array covers
+        # (own interior + the halo cells the reference's following sync fills), vel_ssh.f90:28-36
+        wide = SwcuDims(max(dims.bnd_x1, 3), min(dims.bnd_x2, basin.nx - 2),
+                        max(dims.bnd_y1, 3), min(dims.bnd_y2, basin.ny - 2),
+                        dims.bnd_x1, dims.bnd_x2, dims.bnd_y1, dims.bnd_y2)
+        ssh = np.zeros(shape, dtype=np.float64)
+        check(L.swh_gaussian(C.byref(wide), _ptr(f["lu"]), _ptr(ssh), 1.0, basin.nx // 2, basin.ny // 2))
+        f["ssh"] = ssh
+        f["sshp"] = ssh.copy()
+        f["sshn"] = ssh.copy()
+        for n in ("ubrtr", "ubrtrn", "ubrtrp", "vbrtr", "vbrtrn", "vbrtrp"):
+            f[n] = np.zeros(shape, dtype=np.float64)
+        # init_data.f90:76-77: mu is filled with lvisc_2 and immediately zeroed (keep_mu skips the zeroing)
+        f["mu"] = np.full(shape, sw.lvisc_2 if keep_mu else 0.0, dtype=np.float64)
+        if sw.use_tracers > 0:  # init_data.f90:80-90
+            ff = np.zeros(shape, dtype=np.float64)
+            check(L.swh_gaussian(C.byref(wide), _ptr(f["lu"]), _ptr(ff), 0.5, basin.nx // 2, basin.ny // 2))
+            f["ff1"], f["ff1n"], f["ff1p"] = ff, ff.copy(), ff.copy()
+
+
+# ----------------------------------------------------------------------------- device context
+class DeviceBlock:
+    """One block resident on one GPU (Level B of include/swcuda.h)."""
+
+    def __init__(self, dims: SwcuDims, sw: SwPar, device=0, mode=MODE_FUSED):
+        self.L = _lib.lib()
+        self.dims = dims
+        self.sw = sw
+        self.mode = mode
+        self.params = SwcuParams(sw.full_free_surface, sw.trans_terms, sw.ksw_lat, sw.time_smooth,
+                                 1 if sw.use_tracers > 0 else 0, mode)
+        h = C.c_void_p()
+        check(self.L.swcu_create(C.byref(h), C.byref(dims), C.byref(self.params), device))
+        self.h = h
+
+    def upload(self, name, arr):
+        want = np.float64 if name in F8_NAMES else np.float32
+        a = np.ascontiguousarray(arr, dtype=want)
+        assert a.shape == self.dims.shape, (name, a.shape, self.dims.shape)
+        check(self.L.swcu_upload(self.h, FIELD_ID[name], _ptr(a)))
+        check(self.L.swcu_synchronize(self.h, None))
+
+    def upload_ptr(self, name, host_ptr):
+        """Asynchronous upload from a (pinned) host pointer; caller keeps the buffer alive."""
+        check(self.L.swcu_upload(self.h, FIELD_ID[name], C.c_void_p(host_ptr)))
+
+    def download(self, name, out=None):
+        want = np.float64 if name in F8_NAMES else np.float32
+        if out is None:
+            out = np.empty(self.dims.shape, dtype=want)
+        check(self.L.swcu_download(self.h, FIELD_ID[name], _ptr(out)))
+        return out
+
+    def download_ptr(self, name, host_ptr):
+        check(self.L.swcu_download(self.h, FIELD_ID[name], C.c_void_p(host_ptr)))
+
+    def upload_inputs(self, inp: BlockInputs):
+        for name, arr in inp.f.items():
+            if name == "r_diss" and not arr.any():
+                continue  # the reference never assigns r_diss (core/ocean.f90:32)
+            self.upload(name, arr)
+        self.hh_init()
+
+    def hh_init(self):
+        """envoke(hh_init) of init_ocean_data (control/init_data.f90:60-63); no-op in FUSED mode."""
+        check(self.L.swcu_envoke_hh_init(self.h))
+
+    def step(self, tau, nsteps=1):
+        check(self.L.swcu_step(self.h, float(tau), int(nsteps)))
+
+    def synchronize(self):
+        bad = C.c_long()
+        check(self.L.swcu_synchronize(self.h, C.byref(bad)))
+        return bad.value
+
+    def timer_start(self):
+        check(self.L.swcu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.L.swcu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches(self):
+        return self.L.swcu_launch_count(self.h)
+
+    @property
+    def device_bytes(self):
+        return self.L.swcu_device_bytes(self.h)
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self.L.swcu_comm_init(self.h, nranks, rank, buf))
+
+    def halo_exchange(self, name):
+        check(self.L.swcu_halo_exchange(self.h, FIELD_ID[name]))
+
+    def close(self):
+        if self.h:
+            self.L.swcu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    check(_lib.lib().swcu_comm_unique_id(buf))
+    return buf.raw
+
+
+# ----------------------------------------------------------------------------- the model
+class ShallowWaterModel:
+    """`program model` restricted to the shallow-water path (model.f90:47-200): one block per GPU,
+    y-slabs (parallel.par bppnx = 1, bppny = world size)."""
+
+    def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, mask=None,
+                 device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0):
+        self.basin = basin or BasinPar()
+        self.sw = sw or SwPar()
+        self.run = run or RunPar()
+        self.rank, self.world = rank, world
+        if mask is None and self.basin.mask_file_name != "none":
+            mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
+        self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
+        self.inputs = BlockInputs(self.basin, self.sw, self.dims, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
+                                  r_diss=r_diss)
+        self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode)
+        self.block.upload_inputs(self.inputs)
+        self.tau = self.run.tau
+        self.num_step = 0
+
+    @classmethod
+    def from_par_dir(cls, path, **kw):
+        return cls(BasinPar.from_file(os.path.join(path, "basin.par")), SwPar.from_file(os.path.join(path, "sw.par")),
+                   RunPar.from_file(os.path.join(path, "ocean_run.par")), **kw)
+
+    def attach_comm(self, unique_id):
+        self.block.comm_init(self.world, self.rank, unique_id)
+
+    def expl_shallow_water(self, nsteps=1):
+        self.block.step(self.tau, nsteps)
+        self.num_step += nsteps
+
+    step = expl_shallow_water
+
+    def get(self, name):
+        return self.block.download(name)
+
+    @property
+    def cells_per_step(self):
+        d = self.dims
+        return (d.nx_end - d.nx_start + 1) * (d.ny_end - d.ny_start + 1)

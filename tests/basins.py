@@ -1,0 +1,38 @@
+"""Small deterministic basins shared by the tests (pure integer functions, no RNG state)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def frame_mask(nx, ny):
+    m = np.ones((ny, nx), dtype=np.int32)
+    m[2:ny - 2, 2:nx - 2] = 0
+    return m
+
+
+def island_mask(nx, ny, seed=20240229, ndisc=6, coast=True):
+    """2-cell land frame + discs from an LCG + a sinusoidal coast."""
+    m = frame_mask(nx, ny)
+    s = seed
+    jj, ii = np.mgrid[0:ny, 0:nx]
+    for _ in range(ndisc):
+        s = (1103515245 * s + 12345) % (1 << 31); cx = s % nx
+        s = (1103515245 * s + 12345) % (1 << 31); cy = s % ny
+        s = (1103515245 * s + 12345) % (1 << 31); r = 2 + s % max(3, min(nx, ny) // 10)
+        m[(ii - cx) ** 2 + (jj - cy) ** 2 <= r * r] = 1
+    if coast:
+        depth = (2 + (ny // 8) * (1 + np.sin(ii[0] * (6.0 / nx)))).astype(np.int64)
+        m[jj < depth[None, :]] = 1
+    # never cover the centre of the Gaussian bump completely
+    m[ny // 2 - 1:ny // 2 + 2, nx // 2 - 1:nx // 2 + 2] = 0
+    m[:2, :] = 1; m[-2:, :] = 1; m[:, :2] = 1; m[:, -2:] = 1
+    return m
+
+
+def bs_mask():
+    """The reference's data/BS/mask_bs4km.txt (289x163), packed by tests/golden/make_fixtures.py."""
+    z = np.load(os.path.join(GOLDEN, "bs4km_mask.npz"))
+    nx, ny = int(z["nx"]), int(z["ny"])
+    return np.unpackbits(z["bits"])[: nx * ny].reshape(ny, nx).astype(np.int32)

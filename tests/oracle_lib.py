@@ -123,3 +123,22 @@ class OracleModel:
             self.close()
         except Exception:
             pass
+
+
+def call_kernel(name, dims, *args, fast=False):
+    """Calls oracle kernel `swo_<name>(8 ints, ...)`: numpy arrays go as pointers, Python floats as
+    double, ints as int.  `dims` is an 8-tuple (nx_start, nx_end, ny_start, ny_end, bnd_x1..bnd_y2)."""
+    fn = getattr(lib(fast), "swo_" + name)
+    cargs = [C.c_int(int(v)) for v in dims]
+    for a in args:
+        if isinstance(a, np.ndarray):
+            assert a.flags["C_CONTIGUOUS"]
+            cargs.append(a.ctypes.data_as(C.c_void_p))
+        elif isinstance(a, float):
+            cargs.append(C.c_double(a))
+        elif isinstance(a, (int, np.integer)):
+            cargs.append(C.c_int(int(a)))
+        else:
+            raise TypeError(type(a))
+    fn.restype = C.c_int
+    return fn(*cargs)

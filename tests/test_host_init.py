@@ -1,0 +1,96 @@
+"""CPU tests of the product's host layer: C++ input construction (csrc/sw_host.cpp) and the Python
+mirror of the .par configs / decomposition, checked bitwise against the oracle's independent
+restatement of the same reference code."""
+import os
+
+import numpy as np
+import pytest
+
+import basins
+from ocean_model_arch_b200 import model
+from oracle_lib import OracleModel, make_config
+
+F4 = ["lu", "luu", "luh", "lcu", "lcv", "llu", "llv", "dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb", "rlh_s"]
+
+
+@pytest.mark.parametrize("curve_grid", [0, 1])
+@pytest.mark.parametrize("masked", [False, True])
+def test_single_block_inputs_match_oracle_bitwise(swlib, curve_grid, masked):
+    nx, ny = 68, 52
+    mask = basins.island_mask(nx, ny) if masked else None
+    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=curve_grid)
+    inp = model.BlockInputs(bp, model.SwPar(), model.block_dims(nx, ny, 1, 1, 0, 0), mask)
+    o = OracleModel(make_config(nx, ny, curve_grid=curve_grid), mask)
+    for f in F4 + ["ssh", "sshp", "hhq_rest", "mu", "ubrtr"]:
+        assert np.array_equal(inp.f[f], o.get(f)), f
+
+
+def test_bs4km_inputs_match_oracle_bitwise(swlib):
+    mask = basins.bs_mask()
+    bp = model.BasinPar(nx=289, ny=163, dxst=0.05, dyst=0.04, rlon=27.525, rlat=40.94)
+    inp = model.BlockInputs(bp, model.SwPar(), model.block_dims(289, 163, 1, 1, 0, 0), mask)
+    o = OracleModel(make_config(289, 163, dxst=0.05, dyst=0.04, rlon=27.525, rlat=40.94), mask)
+    for f in F4 + ["ssh"]:
+        assert np.array_equal(inp.f[f], o.get(f)), f
+
+
+def test_slab_blocks_match_oracle_blocks(swlib):
+    """y-slab decomposition (bppnx=1, bppny=G): interior + width-1 halo of every block equals the
+    oracle's block arrays (which restate core/decomposition.f90 + the halo syncs)."""
+    nx, ny, G = 52, 70, 3
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, bnx=1, bny=G), mask)
+    bp = model.BasinPar(nx=nx, ny=ny)
+    for r in range(G):
+        d = model.block_dims(nx, ny, 1, G, 0, r)
+        assert list(d.as_tuple()) == o.block_dims(r)
+        inp = model.BlockInputs(bp, model.SwPar(), d, mask)
+        glob = {f: o.get(f) for f in F4 + ["ssh"]}
+        for f in F4 + ["ssh"]:
+            # rows/cols the reference defines for this block: start-1 .. end+1
+            a = inp.f[f][1:-1, 1:-1]
+            b = glob[f][d.bnd_y1:d.bnd_y2 - 1, d.bnd_x1:d.bnd_x2 - 1]
+            assert np.array_equal(a, b), (r, f)
+
+
+def test_par_files_and_time_manager(tmp_path):
+    (tmp_path / "basin.par").write_text("\n".join([
+        "1525 : nx", "1115 : ny", "1 : nz", "0 : px", "0 : py", "0.00312d0 : dx", "0.00225d0 : dy",
+        "34.751560d0 : rlon", "44.801125d0 : rlat", "0 : xgr", "0 : ygr", "1 : curve", "0.0d0 : rot", "0.0d0 :",
+        "90.0d0 :", "60.0d0 :", "90.0d0 :", "-90.0d0 :", "none : mask", "none : topo"]))
+    (tmp_path / "sw.par").write_text("\n".join(["1 : ffs", "1 : trans", "1 : ksw", "0.5d0 : ts", "1.0d+03 : lvisc",
+                                                "0 : tracers", "1 : n", "none : ssh file"]))
+    (tmp_path / "ocean_run.par").write_text("0 : start\n1.0d0 : step\n0.007 : days\n0 : n\n")
+    (tmp_path / "parallel.par").write_text("0 : mod\nnone : file\n1 : bx\n1 : by\n")
+    b = model.BasinPar.from_file(tmp_path / "basin.par")
+    assert (b.nx, b.ny, b.curve_grid, b.mask_file_name) == (1525, 1115, 1, "none")
+    assert b == model.BasinPar()                      # defaults are the shipped basin.par
+    s = model.SwPar.from_file(tmp_path / "sw.par")
+    assert s == model.SwPar()
+    r = model.RunPar.from_file(tmp_path / "ocean_run.par")
+    assert r.tau == 1.0 and r.num_step_max == 604
+    p = model.ParallelPar.from_file(tmp_path / "parallel.par")
+    assert (p.mod_decomposition, p.bppnx, p.bppny) == (0, 1, 1)
+
+
+def test_mask_file_reader(tmp_path):
+    nx, ny = 12, 9
+    m = basins.island_mask(nx, ny, ndisc=1, coast=False)
+    rows = ["comment"] + ["".join(str(v) for v in m[n]) for n in range(ny - 1, -1, -1)]
+    p = tmp_path / "mask.txt"
+    p.write_text("\n".join(rows) + "\n")
+    assert np.array_equal(model.read_mask_file(p, nx, ny), m)
+
+
+def test_uniform_split_matches_reference_rule(swlib):
+    # core/decomposition.f90:441-458: floor((N - done)/(blocks left)), last block takes the rest
+    for n, nb in [(100, 3), (8192, 8), (1111, 7), (5, 5)]:
+        tot = 0
+        for i in range(nb):
+            d = model.block_dims(n + 4, 9, nb, 1, i, 0)
+            assert d.nx_start == 3 + tot
+            size = d.nx_end - d.nx_start + 1
+            expect = n - tot if i == nb - 1 else (n - tot) // (nb - i)
+            assert size == expect
+            tot += size
+        assert tot == n
