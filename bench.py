@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point-updates/s of the fp64 shallow-water step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S] [--mode fused|reference]
+
+One "step" = one expl_shallow_water(tau) over the whole basin (all K1..K11 work, all physics flags
+of the shipped sw.par on).  Workload = BASELINE.json configs[1]: synthetic rectangular basin of
+S x S computational cells (default 2048), flat 100 m bottom, Gaussian initial SSH, one block per
+GPU; with N GPUs the basin is S x (N*S) cells cut into N y-slabs (weak scaling, per-GPU work
+fixed), halos exchanged every step with ncclSend/ncclRecv.  Prints ONE JSON line on rank 0.
+
+ value      : cells * steps / time, fields resident in HBM, CUDA events on the context's stream,
+              barrier + synchronize on both sides, max over ranks.
+ e2e        : same metric through the C ABI with HOST buffers: every step uploads the six
+              prognostic arrays from pinned host memory and downloads ssh, ubrtr, vbrtr.
+ roofline   : dominant kernel (fused update), algorithmic bytes / its mean launch time measured
+              with CUDA events around every launch in a second timed pass of the same K steps.
+ cpu_baseline: the CPU oracle (a C port of the reference's kernels, -O3 -march=native -fopenmp,
+              one block per thread like _MPP_BLOCK_MODE_) timed on this box's host cores, N=1 only.
+
+--impl reference times that same CPU port as the reference arm (the reference is Fortran + MPI and
+cannot be built in this image).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid-point-updates/s (fp64 SW step)"
+UNIT = "grid-point-updates/s"
+# algorithmic bytes per cell (distinct external arrays read once + written once), DESIGN.md section 4
+B_UPDATE = 6 * 8 + 8 + 8 + 6 * 8 + 8 * 4 + 4 + 1 + 6 * 8   # state, hhq_rest, mu, scratch, metrics, rlh_s, mask, out
+B_PREP = 5 * 8 + 8 + 8 * 4 + 1 + 6 * 8                      # ssh,u,v,up,vp, hhq_rest, metrics, mask, scratch out
+B_REF_STEP = 1196                                            # SURVEY.md 8d, the reference's 11-kernel granularity
+B_MIN_STEP = 196                                             # SURVEY.md 8d, floor for any implementation
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_port_rate(size, steps, warmup, budget_s=25.0):
+    """Times the CPU oracle (-O3 -march=native -fopenmp build made on THIS box) on the same basin:
+    one block per thread (y-slabs), omp-for over blocks per kernel + halo copies, like the
+    reference's _MPP_BLOCK_MODE_ (core/kernel_interface.f90:84-101).  Returns (cells/s, info)."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    subprocess.check_call(["make", "-B", "-C", os.path.join(ROOT, "oracle"), "libsw_oracle_fast.so"],
+                          stdout=subprocess.DEVNULL)
+    from oracle_lib import OracleModel, make_config
+    nthreads = cpu_threads()
+    bny = max(1, min(nthreads, size // 8))
+    n = size + 4
+    m = OracleModel(make_config(n, n, bnx=1, bny=bny, nthreads=nthreads), None, fast=True)
+    t0 = time.perf_counter()
+    m.step(max(1, warmup))
+    per = (time.perf_counter() - t0) / max(1, warmup)
+    if steps is None:
+        steps = int(max(2, min(200, budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    m.step(steps)
+    dt = time.perf_counter() - t0
+    cells = size * size
+    info = {"cores": nthreads, "blocks": f"1x{bny}", "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "sample": f"{steps} steps of the {size}x{size} basin, {bny} y-slab blocks on {nthreads} threads"}
+    m.close()
+    return cells * steps / dt, info
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    rate, info = cpu_port_rate(args.size, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": info["steps"], "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CPU path restated in C (oracle/sw_oracle.c); the Fortran+MPI reference cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"synthetic rectangular basin {args.size}x{args.size} cells per GPU, flat 100 m bottom, "
+                        f"Gaussian SSH, full_free_surface=1 trans_terms=1 ksw_lat=1 (shipped sw.par), tau=1s",
+            "global_cells": [args.size, args.size * n_gpus], "decomposition": f"1x{n_gpus} y-slabs, one block per GPU",
+            "mode": args.mode, "l2": "working set > 126 MB L2 (12 ping-pong + 8 fp64 planes); no flush needed"
+            if args.size >= 1536 else "working set may fit L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=2048, help="computational cells per GPU along each axis")
+    ap.add_argument("--mode", default="fused", choices=["fused", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.steps is None:
+        args.steps = 500
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from ocean_model_arch_b200 import build, model
+    from ocean_model_arch_b200._lib import MODE_FUSED, MODE_REFERENCE
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    S = args.size
+    nx, ny = S + 4, S * world + 4
+    mode = MODE_FUSED if args.mode == "fused" else MODE_REFERENCE
+    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=1 if ny < 20000 else 0)
+    m = model.ShallowWaterModel(bp, model.SwPar(), model.RunPar(), device=local_rank, mode=mode, rank=rank, world=world)
+    if world > 1:
+        ids = [model.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        m.attach_comm(ids[0])
+    blk = m.block
+    cells = m.cells_per_step
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident run: the headline `value`
+    m.step(args.warmup)
+    assert blk.synchronize() == 0
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = blk.launches
+    blk.timer_start()
+    m.step(args.steps)
+    ms = blk.timer_stop()
+    launches = blk.launches - l0
+    assert blk.synchronize() == 0
+    barrier()
+    clocks = sampler.result()
+    ms = max_over_ranks(ms)
+    value = cells * world * args.steps / (ms * 1e-3)
+
+    # ---- second pass of the same K steps with CUDA events around every launch -> per-kernel time
+    roof = None
+    peak, peak_src = peaks()
+    if mode == MODE_FUSED:
+        L = blk.L
+        t_prep, t_upd, n_prep, n_upd = C.c_float(), C.c_float(), C.c_long(), C.c_long()
+        rc = L.swcu_profile_steps(blk.h, C.c_double(m.tau), min(args.steps, 200), C.byref(t_prep), C.byref(n_prep),
+                                  C.byref(t_upd), C.byref(n_upd))
+        if rc == 0 and n_upd.value:
+            d = m.dims
+            upd_cells = (d.nx_end - d.nx_start + 1) * (d.ny_end - d.ny_start + 1)
+            prep_cells = (d.nx_end - d.nx_start + 3) * (d.ny_end - d.ny_start + 3)
+            steps_prof = n_prep.value
+            upd_ms = t_upd.value / steps_prof      # all update launches of a step (strips + interior)
+            prep_ms = t_prep.value / steps_prof
+            ach = B_UPDATE * upd_cells / (upd_ms * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("k_update", {}).get(str(S))
+            roof = {"bound": "hbm", "kernel": "k_update (K1+K4+K6+K7+K8+K11 fused)", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                    "bytes_per_cell": B_UPDATE, "cells_per_launch": upd_cells, "ms_per_launch": upd_ms,
+                    "other_kernels": {"k_prep (K10/K2+K3+K5 fused)": {
+                        "bytes_per_cell": B_PREP, "cells_per_launch": prep_cells, "ms_per_launch": prep_ms,
+                        "achieved": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9,
+                        "frac": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9 / peak}},
+                    "step_bytes_per_cell_launched": B_UPDATE + B_PREP,
+                    "step_frac_launched": (B_UPDATE + B_PREP) * (value / world) / 1e9 / peak,
+                    "step_frac_vs_reference_granularity_1196B": B_REF_STEP * (value / world) / 1e9 / peak,
+                    "step_frac_vs_floor_196B": B_MIN_STEP * (value / world) / 1e9 / peak}
+    else:
+        roof = {"bound": "hbm", "kernel": "11-kernel reference sequence (whole step)", "achieved":
+                B_REF_STEP * (value / world) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": B_REF_STEP * (value / world) / 1e9 / peak, "traffic": None, "peak_source": peak_src}
+
+    # ---- end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        shape = m.dims.shape
+        names_in = ("ssh", "sshp", "ubrtr", "ubrtrp", "vbrtr", "vbrtrp")
+        names_out = ("ssh", "ubrtr", "vbrtr")
+        pin = {n: torch.empty(shape, dtype=torch.float64).pin_memory() for n in names_in}
+        for n in names_in:
+            blk.download_ptr(n, pin[n].data_ptr())
+        e2e_steps = max(3, min(args.steps, 20))
+        def one():
+            for n in names_in:
+                blk.upload_ptr(n, pin[n].data_ptr())
+            m.step(1)
+            for n in names_out:
+                blk.download_ptr(n, pin[n].data_ptr())   # synchronises the stream
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        blk.timer_start()
+        for _ in range(e2e_steps):
+            one()
+        ems = blk.timer_stop()
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = max_over_ranks(max(ems, wall))
+        plane = shape[0] * shape[1] * 8
+        e2e = {"value": cells * world * e2e_steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 6 * plane,
+               "d2h_bytes_per_step": 3 * plane, "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+               "note": "per step: upload 6 prognostic arrays from pinned host memory, 1 step, download ssh/ubrtr/vbrtr"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, info = cpu_port_rate(S, None, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"],
+               "ms_per_step": info["ms_per_step"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "device_bytes": blk.device_bytes}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        blk.close()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

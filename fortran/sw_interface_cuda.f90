@@ -1,0 +1,230 @@
+!-----------------------------------------------------------------------------------------------
+! sw_interface_cuda.f90 -- thin iso_c_binding shim that plugs libswcuda.so (include/swcuda.h) into
+! the reference's algorithm layer in place of gpu/interface/sw_interface_gpu.f90 +
+! gpu/kernel/*.f90.  SOURCE ONLY: this image has no Fortran compiler, so the file is not built or
+! tested here (the same C ABI is exercised through ctypes in tests/).  Nothing in the reference's
+! algorithm layer (control/, core/) changes except the three call sites listed in INTEGRATION.md.
+!
+!   swcuda_c_binding                      bind(C) interfaces of the C ABI
+!   shallow_water_interface_cuda_module   init_device_data_cuda, expl_shallow_water_cuda,
+!                                         download_ssh_cuda, finalize_device_data_cuda
+!
+! One MPI rank drives one GPU and owns one block (parallel.par: bppnx = 1, bppny = 1 per rank on a
+! 1 x nranks process grid, i.e. y-slabs).  Halo exchange happens inside swcu_step over NCCL.
+!-----------------------------------------------------------------------------------------------
+module swcuda_c_binding
+    use iso_c_binding
+    implicit none
+
+    integer(c_int), parameter :: SWCU_OK = 0
+    integer(c_int), parameter :: SWCU_MODE_REFERENCE = 0, SWCU_MODE_FUSED = 1
+
+    ! enum swcu_field (include/swcuda.h)
+    integer(c_int), parameter :: SWCU_F_SSH = 0, SWCU_F_SSHN = 1, SWCU_F_SSHP = 2,                &
+                                 SWCU_F_UBRTR = 3, SWCU_F_UBRTRN = 4, SWCU_F_UBRTRP = 5,          &
+                                 SWCU_F_VBRTR = 6, SWCU_F_VBRTRN = 7, SWCU_F_VBRTRP = 8,          &
+                                 SWCU_F_RHSX = 9, SWCU_F_RHSY = 10, SWCU_F_MU = 15,               &
+                                 SWCU_F_HHQ_REST = 19, SWCU_F_FF1 = 34, SWCU_F_FF1N = 35, SWCU_F_FF1P = 36
+    integer(c_int), parameter :: SWCU_F_LU = 100, SWCU_F_LUU = 101, SWCU_F_LUH = 102, SWCU_F_LCU = 103,  &
+                                 SWCU_F_LCV = 104, SWCU_F_LLU = 105, SWCU_F_LLV = 106,                   &
+                                 SWCU_F_DX = 107, SWCU_F_DY = 108, SWCU_F_DXT = 109, SWCU_F_DYT = 110,   &
+                                 SWCU_F_DXH = 111, SWCU_F_DYH = 112, SWCU_F_DXB = 113, SWCU_F_DYB = 114, &
+                                 SWCU_F_RLH_S = 115, SWCU_F_R_DISS = 116
+
+    type, bind(C) :: swcu_dims
+        integer(c_int) :: nx_start, nx_end, ny_start, ny_end
+        integer(c_int) :: bnd_x1, bnd_x2, bnd_y1, bnd_y2
+    end type
+
+    type, bind(C) :: swcu_params
+        integer(c_int) :: full_free_surface, trans_terms, ksw_lat
+        real(c_double) :: time_smooth
+        integer(c_int) :: use_tracers
+        integer(c_int) :: mode
+    end type
+
+    interface
+        function swcu_create(ctx, dims, params, device) bind(C, name="swcu_create") result(rc)
+            import :: c_ptr, c_int, swcu_dims, swcu_params
+            type(c_ptr), intent(out) :: ctx
+            type(swcu_dims), intent(in) :: dims
+            type(swcu_params), intent(in) :: params
+            integer(c_int), value :: device
+            integer(c_int) :: rc
+        end function
+        function swcu_destroy(ctx) bind(C, name="swcu_destroy") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int) :: rc
+        end function
+        function swcu_upload(ctx, field, host) bind(C, name="swcu_upload") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            type(c_ptr), value :: host
+            integer(c_int) :: rc
+        end function
+        function swcu_download(ctx, field, host) bind(C, name="swcu_download") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: field
+            type(c_ptr), value :: host
+            integer(c_int) :: rc
+        end function
+        function swcu_envoke_hh_init(ctx) bind(C, name="swcu_envoke_hh_init") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int) :: rc
+        end function
+        function swcu_step(ctx, tau, nsteps) bind(C, name="swcu_step") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: ctx
+            real(c_double), value :: tau
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function swcu_synchronize(ctx, bad_cells) bind(C, name="swcu_synchronize") result(rc)
+            import :: c_ptr, c_int, c_long
+            type(c_ptr), value :: ctx
+            integer(c_long), intent(out) :: bad_cells
+            integer(c_int) :: rc
+        end function
+        function swcu_comm_unique_id(id128) bind(C, name="swcu_comm_unique_id") result(rc)
+            import :: c_char, c_int
+            character(kind=c_char), intent(out) :: id128(128)
+            integer(c_int) :: rc
+        end function
+        function swcu_comm_init(ctx, nranks, rank, id128) bind(C, name="swcu_comm_init") result(rc)
+            import :: c_ptr, c_char, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: nranks, rank
+            character(kind=c_char), intent(in) :: id128(128)
+            integer(c_int) :: rc
+        end function
+        function swcu_last_error() bind(C, name="swcu_last_error") result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        ! Level A (per-kernel) entry points take CUDA-Fortran device arrays via c_devloc(); their
+        ! interfaces follow the same pattern, e.g.
+        !   swcu_sw_update_ssh_kernel(dims, tau, lu, dx, dy, dxh, dyh, hhu, hhv, sshn, sshp, u, v, stream)
+        ! in the argument order of kernel/shallow_water/vel_ssh.f90:69-70.
+    end interface
+end module swcuda_c_binding
+
+
+module shallow_water_interface_cuda_module
+    use iso_c_binding
+    use swcuda_c_binding
+    use kind_module, only: wp8 => SHR_KIND_R8, wp4 => SHR_KIND_R4
+    use mpp_module
+    use decomposition_module, only: domain_type, domain => domain_data
+    use ocean_module, only: ocean_type, ocean_data
+    use grid_module, only: grid_type, grid_data
+    use config_sw_module, only: full_free_surface, time_smooth, trans_terms, ksw_lat, use_tracers
+    use errors_module, only: abort_model
+    implicit none
+    save
+    private
+
+    type(c_ptr), allocatable :: ctx(:)      ! one resident context per local block
+
+    public :: init_device_data_cuda, expl_shallow_water_cuda, download_ssh_cuda, finalize_device_data_cuda
+
+contains
+
+    subroutine check(rc, what)
+        integer(c_int), intent(in) :: rc
+        character(*), intent(in) :: what
+        if (rc /= SWCU_OK) call abort_model('swcuda: '//what)      ! shared/errors.f90:30-37
+    end subroutine
+
+    subroutine up8(k, field, a)
+        integer, intent(in) :: k
+        integer(c_int), intent(in) :: field
+        real(wp8), target, intent(in) :: a(:, :)
+        call check(swcu_upload(ctx(k), field, c_loc(a)), 'upload')
+    end subroutine
+
+    subroutine up4(k, field, a)
+        integer, intent(in) :: k
+        integer(c_int), intent(in) :: field
+        real(wp4), target, intent(in) :: a(:, :)
+        call check(swcu_upload(ctx(k), field, c_loc(a)), 'upload')
+    end subroutine
+
+    ! replaces init_device_data (control/init_data.f90:127-145): called once after init_grid_data /
+    ! init_ocean_data have filled the host arrays
+    subroutine init_device_data_cuda()
+        type(swcu_dims) :: d
+        type(swcu_params) :: p
+        character(kind=c_char) :: id(128)
+        integer :: k, ierr
+
+        allocate(ctx(domain%bcount))
+        p%full_free_surface = full_free_surface; p%trans_terms = trans_terms; p%ksw_lat = ksw_lat
+        p%time_smooth = time_smooth; p%use_tracers = use_tracers; p%mode = SWCU_MODE_FUSED
+        if (use_tracers > 0) p%mode = SWCU_MODE_REFERENCE
+        do k = 1, domain%bcount
+            d%nx_start = domain%bnx_start(k); d%nx_end = domain%bnx_end(k)
+            d%ny_start = domain%bny_start(k); d%ny_end = domain%bny_end(k)
+            d%bnd_x1 = domain%bbnd_x1(k); d%bnd_x2 = domain%bbnd_x2(k)
+            d%bnd_y1 = domain%bbnd_y1(k); d%bnd_y2 = domain%bbnd_y2(k)
+            call check(swcu_create(ctx(k), d, p, int(k - 1, c_int)), 'create')
+            call up4(k, SWCU_F_LU,  grid_data%lu %block(k)%field); call up4(k, SWCU_F_LUU, grid_data%luu%block(k)%field)
+            call up4(k, SWCU_F_LUH, grid_data%luh%block(k)%field); call up4(k, SWCU_F_LCU, grid_data%lcu%block(k)%field)
+            call up4(k, SWCU_F_LCV, grid_data%lcv%block(k)%field); call up4(k, SWCU_F_LLU, grid_data%llu%block(k)%field)
+            call up4(k, SWCU_F_LLV, grid_data%llv%block(k)%field)
+            call up4(k, SWCU_F_DX,  grid_data%dx %block(k)%field); call up4(k, SWCU_F_DY,  grid_data%dy %block(k)%field)
+            call up4(k, SWCU_F_DXT, grid_data%dxt%block(k)%field); call up4(k, SWCU_F_DYT, grid_data%dyt%block(k)%field)
+            call up4(k, SWCU_F_DXH, grid_data%dxh%block(k)%field); call up4(k, SWCU_F_DYH, grid_data%dyh%block(k)%field)
+            call up4(k, SWCU_F_DXB, grid_data%dxb%block(k)%field); call up4(k, SWCU_F_DYB, grid_data%dyb%block(k)%field)
+            call up4(k, SWCU_F_RLH_S, grid_data%rlh_s%block(k)%field)
+            call up8(k, SWCU_F_HHQ_REST, grid_data%hhq_rest%block(k)%field)
+            call up8(k, SWCU_F_SSH,    ocean_data%ssh   %block(k)%field); call up8(k, SWCU_F_SSHP,   ocean_data%sshp  %block(k)%field)
+            call up8(k, SWCU_F_UBRTR,  ocean_data%ubrtr %block(k)%field); call up8(k, SWCU_F_UBRTRP, ocean_data%ubrtrp%block(k)%field)
+            call up8(k, SWCU_F_VBRTR,  ocean_data%vbrtr %block(k)%field); call up8(k, SWCU_F_VBRTRP, ocean_data%vbrtrp%block(k)%field)
+            call up8(k, SWCU_F_MU,     ocean_data%mu    %block(k)%field)
+            call check(swcu_envoke_hh_init(ctx(k)), 'hh_init')
+        enddo
+        ! one NCCL communicator over the y-slab ranks; the id travels over the existing MPI communicator
+        if (mpp_count > 1) then
+            if (mpp_is_master()) call check(swcu_comm_unique_id(id), 'unique_id')
+            call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
+            call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), id), 'comm_init')
+        endif
+    end subroutine
+
+    ! replaces expl_shallow_water_gpu (control/shallow_water/shallow_water.f90:184-251); model.f90:146
+    ! calls it from inside the long-lived !$omp parallel region, so only the master thread launches
+    subroutine expl_shallow_water_cuda(tau)
+        real(wp8), intent(in) :: tau
+        integer :: k
+        !$omp master
+        do k = 1, domain%bcount
+            call check(swcu_step(ctx(k), real(tau, c_double), 1_c_int), 'step')
+        enddo
+        !$omp end master
+        !$omp barrier
+    end subroutine
+
+    ! replaces ocean_data%ssh%sync_host_device(domain, .false.) before local_output (model.f90:181);
+    ! also polls the device-side check_ssh_err flag (K11)
+    subroutine download_ssh_cuda()
+        integer :: k
+        integer(c_long) :: bad
+        do k = 1, domain%bcount
+            call check(swcu_synchronize(ctx(k), bad), 'SIGFPRE predict error')
+            call check(swcu_download(ctx(k), SWCU_F_SSH, c_loc(ocean_data%ssh%block(k)%field)), 'download')
+        enddo
+    end subroutine
+
+    subroutine finalize_device_data_cuda()
+        integer :: k
+        do k = 1, size(ctx)
+            call check(swcu_destroy(ctx(k)), 'destroy')
+        enddo
+        deallocate(ctx)
+    end subroutine
+
+end module shallow_water_interface_cuda_module

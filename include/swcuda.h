@@ -223,6 +223,11 @@ int swcu_synchronize(swcu_ctx *ctx, long *bad_cells);
  * can time the step the way mpp_device_time_model_step does (shared/mpp/mpp.f90:406-423). */
 int swcu_timer_start(swcu_ctx *ctx);
 int swcu_timer_stop(swcu_ctx *ctx, float *elapsed_ms);
+/* Runs nsteps like swcu_step but brackets every kernel launch with CUDA events on the context's
+ * stream and returns the summed device time (ms) and launch count of the two fused kernels
+ * (prep, update).  FUSED mode only; used for per-kernel roofline numbers. */
+int swcu_profile_steps(swcu_ctx *ctx, double tau, int nsteps,
+                       float *prep_ms, long *prep_launches, float *update_ms, long *update_launches);
 /* Launch count of this library's kernels on this context since creation. */
 long swcu_launch_count(const swcu_ctx *ctx);
 /* Bytes of device memory held by the context. */

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "swcu_synchronize": [_P, C.POINTER(C.c_long)],
     "swcu_timer_start": [_P],
     "swcu_timer_stop": [_P, C.POINTER(C.c_float)],
+    "swcu_profile_steps": [_P, _D, _I, C.POINTER(C.c_float), C.POINTER(C.c_long), C.POINTER(C.c_float), C.POINTER(C.c_long)],
     "swcu_launch_count": [_P],
     "swcu_device_bytes": [_P],
     "swcu_stream": [_P],

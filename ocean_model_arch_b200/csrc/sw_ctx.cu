@@ -111,6 +111,10 @@ struct swcu_ctx {
     long steps_done = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // per-launch event pairs, filled only inside swcu_profile_steps
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;  // begin, end, begin, end, ...
+    std::vector<int> prof_kind;        // 0 = prep, 1 = update
 };
 
 namespace {
@@ -199,6 +203,18 @@ int sync_fields(swcu_ctx *c, std::initializer_list<int> fields)
 }
 
 #define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
+
+int prof_mark(swcu_ctx *c, int kind, bool begin)
+{
+    if (!c->prof) return SWCU_OK;
+    cudaEvent_t e;
+    SWCU_CUDA(cudaEventCreate(&e));
+    SWCU_CUDA(cudaEventRecord(e, c->st));
+    c->prof_ev.push_back(e);
+    if (begin) c->prof_kind.push_back(kind);
+    return SWCU_OK;
+}
+#define PROF(kind, call) do { RC(prof_mark(c, kind, true)); RC(call); RC(prof_mark(c, kind, false)); } while (0)
 
 // control/shallow_water/shallow_water.f90:22-94 with the binders' argument choice
 // (interface/shallow_water/sw_interface.f90), then control/tracer.f90:44-61
@@ -304,18 +320,18 @@ int step_fused(swcu_ctx *c, double tau)
     a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;
 
     const int ns = g.ny_start, ne = g.ny_end;
-    RC(launch_prep(g, a, ns - 1, ne + 1, c->st));
+    PROF(0, launch_prep(g, a, ns - 1, ne + 1, c->st));
     c->launches++;
     if (!c->comm) {
-        RC(launch_update(g, a, ns, ne, c->st));
+        PROF(1, launch_update(g, a, ns, ne, c->st));
         c->launches++;
     } else {
         // boundary strips (the two rows each neighbour needs) first, then the exchange on the side
         // stream overlapped with the interior update
         const bool lo = c->rank > 0, hi = c->rank + 1 < c->nranks;
         int i0 = ns, i1 = ne;
-        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(launch_update(g, a, ns, e, c->st)); c->launches++; i0 = e + 1; }
-        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(launch_update(g, a, s, ne, c->st)); c->launches++; i1 = s - 1; }
+        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; PROF(1, launch_update(g, a, ns, e, c->st)); c->launches++; i0 = e + 1; }
+        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; PROF(1, launch_update(g, a, s, ne, c->st)); c->launches++; i1 = s - 1; }
         SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->st));
         SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
         SWCU_NCCL(g_nccl.GroupStart());
@@ -323,7 +339,7 @@ int step_fused(swcu_ctx *c, double tau)
             if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
         SWCU_NCCL(g_nccl.GroupEnd());
         SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
-        if (i0 <= i1) { RC(launch_update(g, a, i0, i1, c->st)); c->launches++; }
+        if (i0 <= i1) { PROF(1, launch_update(g, a, i0, i1, c->st)); c->launches++; }
         SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
     }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
@@ -531,6 +547,34 @@ int swcu_step(swcu_ctx *c, double tau, int nsteps)
         RC(c->p.mode == SWCU_MODE_FUSED ? step_fused(c, tau) : step_reference(c, tau));
         c->steps_done++;
     }
+    return SWCU_OK;
+}
+
+int swcu_profile_steps(swcu_ctx *c, double tau, int nsteps,
+                       float *prep_ms, long *prep_launches, float *update_ms, long *update_launches)
+{
+    if (!c || nsteps < 0 || !prep_ms || !prep_launches || !update_ms || !update_launches) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_FUSED) { set_error("profile_steps needs FUSED mode"); return SWCU_ERR_STATE; }
+    Use use(c->device);
+    c->prof = true;
+    int rc = SWCU_OK;
+    for (int i = 0; i < nsteps && !rc; ++i) { rc = step_fused(c, tau); c->steps_done++; }
+    c->prof = false;
+    cudaError_t e = cudaStreamSynchronize(c->st);
+    float sum[2] = {0.f, 0.f};
+    long cnt[2] = {0, 0};
+    for (size_t k = 0; k < c->prof_kind.size() && 2 * k + 1 < c->prof_ev.size(); ++k) {
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]) == cudaSuccess) {
+            sum[c->prof_kind[k]] += ms;
+            cnt[c->prof_kind[k]]++;
+        }
+    }
+    for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
+    c->prof_ev.clear(); c->prof_kind.clear();
+    *prep_ms = sum[0]; *prep_launches = cnt[0]; *update_ms = sum[1]; *update_launches = cnt[1];
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "profile_steps");
     return SWCU_OK;
 }
 
