@@ -37,6 +37,7 @@ UNIT = "grid-point-updates/s"
 # algorithmic bytes per cell (distinct external arrays read once + written once), DESIGN.md section 4
 B_UPDATE = 6 * 8 + 8 + 8 + 6 * 8 + 8 * 4 + 4 + 1 + 6 * 8   # state, hhq_rest, mu, scratch, metrics, rlh_s, mask, out
 B_PREP = 5 * 8 + 8 + 8 * 4 + 1 + 6 * 8                      # ssh,u,v,up,vp, hhq_rest, metrics, mask, scratch out
+B_TILED = 8 * 8 + 1 + 6 * 8                                  # k_step: ssh,sshp,u,up,v,vp,hhq_rest,mu + mask byte, 6 out
 B_REF_STEP = 1196                                            # SURVEY.md 8d, the reference's 11-kernel granularity
 B_MIN_STEP = 196                                             # SURVEY.md 8d, floor for any implementation
 
@@ -165,6 +166,8 @@ def main():
     ap.add_argument("--mode", default="fused", choices=["fused", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tiled", action="store_true", help="fused mode: two launches per step instead of one")
+    ap.add_argument("--tile-variant", type=int, default=None, help="tiled kernel variant (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -208,6 +211,10 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         m.attach_comm(ids[0])
     blk = m.block
+    if args.no_tiled:
+        blk.set_option("tiled", 0)
+    if args.tile_variant is not None:
+        blk.set_option("tile_variant", args.tile_variant)
     cells = m.cells_per_step
 
     def barrier():
@@ -252,25 +259,30 @@ def main():
             d = m.dims
             upd_cells = (d.nx_end - d.nx_start + 1) * (d.ny_end - d.ny_start + 1)
             prep_cells = (d.nx_end - d.nx_start + 3) * (d.ny_end - d.ny_start + 3)
-            steps_prof = n_prep.value
-            upd_ms = t_upd.value / steps_prof      # all update launches of a step (strips + interior)
-            prep_ms = t_prep.value / steps_prof
-            ach = B_UPDATE * upd_cells / (upd_ms * 1e-3) / 1e9
+            steps_prof = min(args.steps, 200)
+            tiled = n_prep.value == 0
+            upd_ms = t_upd.value / steps_prof      # all launches of that kernel in a step (strips + interior)
+            bpc = B_TILED if tiled else B_UPDATE
+            ach = bpc * upd_cells / (upd_ms * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
+            kname = "k_step" if tiled else "k_update"
             if os.path.exists(tp):
-                traffic = json.load(open(tp)).get("k_update", {}).get(str(S))
-            roof = {"bound": "hbm", "kernel": "k_update (K1+K4+K6+K7+K8+K11 fused)", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                    "bytes_per_cell": B_UPDATE, "cells_per_launch": upd_cells, "ms_per_launch": upd_ms,
-                    "other_kernels": {"k_prep (K10/K2+K3+K5 fused)": {
-                        "bytes_per_cell": B_PREP, "cells_per_launch": prep_cells, "ms_per_launch": prep_ms,
-                        "achieved": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9,
-                        "frac": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9 / peak}},
-                    "step_bytes_per_cell_launched": B_UPDATE + B_PREP,
-                    "step_frac_launched": (B_UPDATE + B_PREP) * (value / world) / 1e9 / peak,
+                traffic = json.load(open(tp)).get(kname, {}).get(str(S))
+            roof = {"bound": "hbm",
+                    "kernel": "k_step (K1..K11 in one TMA-tiled launch)" if tiled else "k_update (K1+K4+K6+K7+K8+K11 fused)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": peak_src, "bytes_per_cell": bpc, "cells_per_launch": upd_cells,
+                    "ms_per_launch": upd_ms, "launches_per_step": n_upd.value / steps_prof,
+                    "step_bytes_per_cell_launched": bpc if tiled else B_UPDATE + B_PREP,
                     "step_frac_vs_reference_granularity_1196B": B_REF_STEP * (value / world) / 1e9 / peak,
                     "step_frac_vs_floor_196B": B_MIN_STEP * (value / world) / 1e9 / peak}
+            if not tiled:
+                prep_ms = t_prep.value / steps_prof
+                roof["other_kernels"] = {"k_prep (K10/K2+K3+K5 fused)": {
+                    "bytes_per_cell": B_PREP, "cells_per_launch": prep_cells, "ms_per_launch": prep_ms,
+                    "achieved": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9,
+                    "frac": B_PREP * prep_cells / (prep_ms * 1e-3) / 1e9 / peak}}
     else:
         roof = {"bound": "hbm", "kernel": "11-kernel reference sequence (whole step)", "achieved":
                 B_REF_STEP * (value / world) / 1e9, "peak": peak, "unit": "GB/s",

@@ -206,6 +206,15 @@ int swcu_download(swcu_ctx *ctx, int field, void *host);
 int swcu_upload_from_device(swcu_ctx *ctx, int field, const void *dev);
 int swcu_download_to_device(swcu_ctx *ctx, int field, void *dev);
 
+/* Tuning / testing knobs.  "metric_tables": 1 (default) = use per-row tables of the metric arrays
+ * when every one of them is constant along m (carthesian and unrotated spherical grids), 0 = always
+ * read the 2-D real(4) arrays.  "tiled": 1 (default) = with metric tables in use, run the whole
+ * step as ONE launch of the TMA-staged shared-memory kernel; 0 = two launches (prep + update) from
+ * global memory.  Results are bitwise identical in every combination. */
+int swcu_set_option(swcu_ctx *ctx, const char *name, int value);
+/* 1 if the last step used the per-row metric tables, 0 if it read the 2-D arrays. */
+int swcu_uses_metric_tables(const swcu_ctx *ctx);
+
 /* The envoke(hh_init) of init_ocean_data (control/init_data.f90:60-63): K10 + its halo sync on the
  * resident arrays, to be called once after the initial uploads.  A no-op in FUSED mode, where the
  * depth fields are functions of the resident state. */

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "swcu_download": [_P, _I, _P],
     "swcu_upload_from_device": [_P, _I, _P],
     "swcu_download_to_device": [_P, _I, _P],
+    "swcu_set_option": [_P, C.c_char_p, _I],
+    "swcu_uses_metric_tables": [_P],
     "swcu_envoke_hh_init": [_P],
     "swcu_step": [_P, _D, _I],
     "swcu_synchronize": [_P, C.POINTER(C.c_long)],

@@ -1,0 +1,118 @@
+// sw_cells.cuh -- the two per-cell stages of the fused step, written once and instantiated over
+// global memory (k_prep / k_update) and over shared-memory tiles (k_step).  All arrays of one
+// `Cell*` view share one index space: element (m,n) at [c], neighbours at c+-1 and c+-p.
+#pragma once
+#include "sw_formulas.cuh"
+
+namespace swcu {
+
+// bit <=> the reference's real(4) mask of the same name is > 0.5 (core/grid.f90:24-31)
+enum : int { MB_LU = 1, MB_LCU = 2, MB_LCV = 4, MB_LUU = 8, MB_LUH = 16, MB_LLU = 32, MB_LLV = 64 };
+
+__device__ __forceinline__ double md(unsigned char bits, int bit) { return (bits & bit) ? 1.0 : 0.0; }
+
+struct PrepOut { double hu, hv, hh, vort, str_t, str_s; };
+
+// Stage A for cell c: K10/K2 depths on U/V/H points (depth.f90:48,57-94), K3 vorticity
+// (vel_ssh.f90:273-275), K5 stresses (mixing.f90:43-51).  Masked-out results are 0, the value the
+// reference's zero-initialised arrays keep where the kernels never store.
+template <bool TRANS, bool LAT, class M>
+__device__ __forceinline__ PrepOut prep_cell(long c, int r, int p, const M &mt, double ffs,
+        const unsigned char *__restrict__ mask,
+        const double *__restrict__ ssh, const double *__restrict__ h_r,
+        const double *__restrict__ u, const double *__restrict__ v,
+        const double *__restrict__ up, const double *__restrict__ vp)
+{
+    const long e = c + 1, no = c + p, en = c + 1 + p;
+    const unsigned char mb = mask[c];
+    const double q_c = h_r[c] + ssh[c] * ffs, q_e = h_r[e] + ssh[e] * ffs;
+    const double q_n = h_r[no] + ssh[no] * ffs, q_en = h_r[en] + ssh[en] * ffs;
+    const double lu_c = md(mb, MB_LU), lu_e = md(mask[e], MB_LU);
+    const double lu_n = md(mask[no], MB_LU), lu_en = md(mask[en], MB_LU);
+    const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r), dx_e = mt.dx(e, r), dy_e = mt.dy(e, r);
+    const double dx_n = mt.dx(no, r + 1), dy_n = mt.dy(no, r + 1), dx_en = mt.dx(en, r + 1), dy_en = mt.dy(en, r + 1);
+    PrepOut o;
+    const double hu = f_interp2(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, mt.dxt(c, r), mt.dyh(c, r));
+    const double hv = f_interp2(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, mt.dxh(c, r), mt.dyt(c, r));
+    const double hh = f_interp4(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
+                                dx_en, dy_en, lu_en, mt.dxb(c, r), mt.dyb(c, r));
+    o.hu = (mb & MB_LLU) ? hu : 0.0;
+    o.hv = (mb & MB_LLV) ? hv : 0.0;
+    o.hh = (mb & MB_LUH) ? hh : 0.0;
+    o.vort = 0.0; o.str_t = 0.0; o.str_s = 0.0;
+    if (TRANS) {
+        const double vo = f_vort(c, r, p, mt, u, v);
+        o.vort = (mb & MB_LUU) ? vo : 0.0;
+    }
+    if (LAT) {
+        const double st = f_str_t(c, r, p, mt, up, vp), ss = f_str_s(c, r, p, mt, up, vp);
+        o.str_t = (mb & MB_LU) ? st : 0.0;
+        o.str_s = (mb & MB_LUU) ? ss : 0.0;
+    }
+    return o;
+}
+
+struct UpdOut { double ssh, sshp, u, up, v, vp; int bad; };
+
+// Stage B for cell c: K1, K4, K6, K7, K8, K11.  Everything is evaluated unconditionally and the
+// masks select at the end (branch-free; masked lanes may carry Inf/NaN that are never stored).
+// rhsx / rhsy / rdx / rdy: RHSx(m,n), RHSy(m,n), dble(rdis(m,n)+rdis(m+1,n)), dble(rdis(m,n)+rdis(m,n+1)).
+template <bool TRANS, bool LAT, class M>
+__device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt, double tau, double ts, double ffs,
+        const unsigned char *__restrict__ mask,
+        const double *__restrict__ ssh, const double *__restrict__ sshp,
+        const double *__restrict__ u, const double *__restrict__ up,
+        const double *__restrict__ v, const double *__restrict__ vp,
+        const double *__restrict__ h_r, const double *__restrict__ mu,
+        const double *__restrict__ hu, const double *__restrict__ hv, const double *__restrict__ hh,
+        const double *__restrict__ vort, const double *__restrict__ str_t, const double *__restrict__ str_s,
+        double rhsx, double rhsy, double rdx, double rdy)
+{
+    const long e = c + 1, no = c + p;
+    const unsigned char mb = mask[c];
+    const double ssh_c = ssh[c], sshp_c = sshp[c];
+    const double u_c = u[c], up_c = up[c], v_c = v[c], vp_c = vp[c];
+    UpdOut o;
+
+    // K1 + K8 + K11
+    const double sshn = f_sshn(c, r, p, tau, mt, hu, hv, sshp, u, v);
+    const bool sea = mb & MB_LU;
+    o.ssh = sea ? sshn : ssh_c;
+    o.sshp = sea ? f_filter(ssh_c, sshn, sshp_c, ts) : sshp_c;  // vel_ssh.f90:230-231
+    o.bad = sea && !(sshn < 10000.0 && sshn > -10000.0);          // vel_ssh.f90:55
+
+    const double h_c = h_r[c];
+    const double q_c = h_c + ssh_c * ffs, qp_c = h_c + sshp_c * ffs;
+    const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r);
+    const double lu_c = md(mb, MB_LU);
+    {   // zonal velocity: K10 (shp), K4, K6, K7, K8
+        const double h_e = h_r[e];
+        const double q_e = h_e + ssh[e] * ffs, qp_e = h_e + sshp[e] * ffs;
+        const double hu_c = hu[c];
+        const double hup_c = f_interp2(qp_c, qp_e, dx_c, dy_c, lu_c, mt.dx(e, r), mt.dy(e, r), md(mask[e], MB_LU),
+                                       mt.dxt(c, r), mt.dyh(c, r));  // depth.f90:62-63
+        const double adv = TRANS ? f_rhsx_adv(c, r, p, mt, md(mb, MB_LUU), md(mask[c - p], MB_LUU),
+                                              u, v, vort, hu, hv, hh) : 0.0;
+        const double dif = LAT ? f_rhsx_dif(c, r, p, mt, q_c, q_e, mu, str_t, str_s, hh) : 0.0;
+        const double un = f_un(c, r, p, tau, mt, hu_c, hu_c, hup_c, rhsx, dif, adv, rdx, hh, ssh, v, up);
+        const bool w = mb & MB_LCU;
+        o.u = w ? un : u_c;
+        o.up = w ? f_filter(u_c, un, up_c, ts) : up_c;
+    }
+    {   // meridional velocity
+        const double h_n = h_r[no];
+        const double q_n = h_n + ssh[no] * ffs, qp_n = h_n + sshp[no] * ffs;
+        const double hv_c = hv[c];
+        const double hvp_c = f_interp2(qp_c, qp_n, dx_c, dy_c, lu_c, mt.dx(no, r + 1), mt.dy(no, r + 1),
+                                       md(mask[no], MB_LU), mt.dxh(c, r), mt.dyt(c, r));  // depth.f90:73-74
+        const double adv = TRANS ? f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh) : 0.0;
+        const double dif = LAT ? f_rhsy_dif(c, r, p, mt, q_c, q_n, mu, str_t, str_s, hh) : 0.0;
+        const double vn = f_vn(c, r, p, tau, mt, hv_c, hv_c, hvp_c, rhsy, dif, adv, rdy, hh, ssh, u, vp);
+        const bool w = mb & MB_LCV;
+        o.v = w ? vn : v_c;
+        o.vp = w ? f_filter(v_c, vn, vp_c, ts) : vp_c;
+    }
+    return o;
+}
+
+}  // namespace swcu

@@ -18,6 +18,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "sw_fused.h"
@@ -71,6 +72,27 @@ int nccl_fail(ncclResult_t r, const char *what)
         if (r__ != ncclSuccess) return nccl_fail(r__, #call);  \
     } while (0)
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int encode_load()
+{
+    if (g_encode) return SWCU_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        cudaGetLastError();
+        return SWCU_ERR_CUDA;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    return SWCU_OK;
+}
+
 const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
 
 int mask_bit(int field)
@@ -111,6 +133,14 @@ struct swcu_ctx {
     long steps_done = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // per-row metric tables (FUSED): rebuilt after a metric upload, used when all arrays are row-constant
+    bool metrics_dirty = true, want_tables = true, use_tables = false;
+    double *tab = nullptr;
+    const float **arr_list_dev = nullptr;
+    int *nonrow_dev = nullptr;
+    bool want_tiled = true;                   // one-launch TMA-tiled step when the tables are usable
+    int tile_variant = 1;
+    std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
     // per-launch event pairs, filled only inside swcu_profile_steps
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;  // begin, end, begin, end, ...
@@ -295,9 +325,65 @@ int step_reference(swcu_ctx *c, double tau)
     return SWCU_OK;
 }
 
+void fill_static_args(swcu_ctx *c, FusedArgs &a)
+{
+    a.dx = F4(c, SWCU_F_DX); a.dy = F4(c, SWCU_F_DY); a.dxt = F4(c, SWCU_F_DXT); a.dyt = F4(c, SWCU_F_DYT);
+    a.dxh = F4(c, SWCU_F_DXH); a.dyh = F4(c, SWCU_F_DYH); a.dxb = F4(c, SWCU_F_DXB); a.dyb = F4(c, SWCU_F_DYB);
+    a.rlh_s = F4(c, SWCU_F_RLH_S); a.rdis = c->has_rdiss ? F4(c, SWCU_F_R_DISS) : nullptr;
+    a.mask = c->mask; a.bad = c->bad_dev;
+}
+
+// (re)builds the per-row metric tables and decides whether they may replace the 2-D arrays
+int prepare_metrics(swcu_ctx *c)
+{
+    c->metrics_dirty = false;
+    c->use_tables = false;
+    if (!c->want_tables) return SWCU_OK;
+    FusedArgs a;
+    fill_static_args(c, a);
+    if (!c->tab) {
+        // + slack: tiles that hang over the top of the array index a few rows past h
+        RC(dev_alloc(c, (void **)&c->tab, ((size_t)T_COUNT * c->h + 64) * sizeof(double)));
+        RC(dev_alloc(c, (void **)&c->arr_list_dev, 9 * sizeof(float *)));
+        RC(dev_alloc(c, (void **)&c->nonrow_dev, sizeof(int)));
+    }
+    const float *list[9] = {a.dx, a.dy, a.dxt, a.dyt, a.dxh, a.dyh, a.dxb, a.dyb, a.rlh_s};
+    SWCU_CUDA(cudaMemcpyAsync(c->arr_list_dev, list, sizeof(list), cudaMemcpyHostToDevice, c->st));
+    SWCU_CUDA(cudaMemsetAsync(c->nonrow_dev, 0, sizeof(int), c->st));
+    RC(launch_build_tables(c->g, a, c->tab, c->h, c->nonrow_dev, c->arr_list_dev, c->st));
+    int nonrow = 1;
+    SWCU_CUDA(cudaMemcpyAsync(&nonrow, c->nonrow_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    c->use_tables = nonrow == 0;
+    return SWCU_OK;
+}
+
+// TMA descriptor of one pitched fp64 plane: dims (w, h), row stride pitch*8 B, box = tile + halo
+int tensor_map_for(swcu_ctx *c, const double *base, CUtensorMap *out)
+{
+    auto it = c->tmaps.find(base);
+    if (it != c->tmaps.end()) { *out = it->second; return SWCU_OK; }
+    RC(encode_load());
+    int bw = 0, bh = 0;
+    step_tile_box(c->tile_variant, &bw, &bh);
+    const cuuint64_t dims[2] = {(cuuint64_t)c->w, (cuuint64_t)c->h};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->pitch * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return SWCU_ERR_CUDA; }
+    c->tmaps[base] = m;
+    *out = m;
+    return SWCU_OK;
+}
+
 int step_fused(swcu_ctx *c, double tau)
 {
     const Geo &g = c->g;
+    if (c->metrics_dirty) RC(prepare_metrics(c));
     if (c->alt_dirty) {  // the frame / land cells of the write buffers must equal the read buffers
         for (int i = 0; i < 6; ++i)
             SWCU_CUDA(cudaMemcpyAsync(c->alt[i], c->f8[kState[i]], c->plane * sizeof(double),
@@ -312,26 +398,37 @@ int step_fused(swcu_ctx *c, double tau)
     a.RHSx = c->has_rhs ? c->f8[SWCU_F_RHSX] : nullptr; a.RHSy = c->has_rhs ? c->f8[SWCU_F_RHSY] : nullptr;
     a.hu = c->f8[SWCU_F_HHU]; a.hv = c->f8[SWCU_F_HHV]; a.hh = c->f8[SWCU_F_HHH];
     a.vort = c->f8[SWCU_F_VORT]; a.str_t = c->f8[SWCU_F_STR_T]; a.str_s = c->f8[SWCU_F_STR_S];
-    a.dx = F4(c, SWCU_F_DX); a.dy = F4(c, SWCU_F_DY); a.dxt = F4(c, SWCU_F_DXT); a.dyt = F4(c, SWCU_F_DYT);
-    a.dxh = F4(c, SWCU_F_DXH); a.dyh = F4(c, SWCU_F_DYH); a.dxb = F4(c, SWCU_F_DXB); a.dyb = F4(c, SWCU_F_DYB);
-    a.rlh_s = F4(c, SWCU_F_RLH_S); a.rdis = c->has_rdiss ? F4(c, SWCU_F_R_DISS) : nullptr;
-    a.mask = c->mask; a.bad = c->bad_dev;
+    fill_static_args(c, a);
+    a.tab = c->use_tables ? c->tab : nullptr; a.tab_h = c->h;
     a.tau = tau; a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
     a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;
 
     const int ns = g.ny_start, ne = g.ny_end;
-    PROF(0, launch_prep(g, a, ns - 1, ne + 1, c->st));
-    c->launches++;
-    if (!c->comm) {
-        PROF(1, launch_update(g, a, ns, ne, c->st));
+    const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(a);
+    StepMaps maps;
+    if (tiled) {
+        const double *src[8] = {a.ssh, a.sshp, a.u, a.up, a.v, a.vp, a.h_r, a.mu};
+        for (int k = 0; k < 8; ++k) RC(tensor_map_for(c, src[k], &maps.m[k]));
+    } else {
+        PROF(0, launch_prep(g, a, ns - 1, ne + 1, c->st));
         c->launches++;
+    }
+    // rows [r0..r1] of the n+1 state: one tiled launch, or the update stage of the two-launch path
+    auto rows = [&](int r0, int r1) -> int {
+        if (r1 < r0) return SWCU_OK;
+        PROF(1, tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, c->st) : launch_update(g, a, r0, r1, c->st));
+        c->launches++;
+        return SWCU_OK;
+    };
+    if (!c->comm) {
+        RC(rows(ns, ne));
     } else {
         // boundary strips (the two rows each neighbour needs) first, then the exchange on the side
         // stream overlapped with the interior update
         const bool lo = c->rank > 0, hi = c->rank + 1 < c->nranks;
         int i0 = ns, i1 = ne;
-        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; PROF(1, launch_update(g, a, ns, e, c->st)); c->launches++; i0 = e + 1; }
-        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; PROF(1, launch_update(g, a, s, ne, c->st)); c->launches++; i1 = s - 1; }
+        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(rows(ns, e)); i0 = e + 1; }
+        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(rows(s, ne)); i1 = s - 1; }
         SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->st));
         SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
         SWCU_NCCL(g_nccl.GroupStart());
@@ -339,7 +436,7 @@ int step_fused(swcu_ctx *c, double tau)
             if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
         SWCU_NCCL(g_nccl.GroupEnd());
         SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
-        if (i0 <= i1) { PROF(1, launch_update(g, a, i0, i1, c->st)); c->launches++; }
+        RC(rows(i0, i1));
         SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
     }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
@@ -393,6 +490,7 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
         }
         if (fused && field == SWCU_F_R_DISS && !c->has_rdiss) { c->has_rdiss = true; RC(alloc4(c, SWCU_F_R_DISS)); }
         if (fused && !fused_keeps4(c, field)) return SWCU_OK;
+        if (field >= SWCU_F_DX && field <= SWCU_F_RLH_S) c->metrics_dirty = true;
         return copy_in(c, F4(c, field), (const float *)src, kind);
     }
     set_error("unknown field id %d", field);
@@ -505,6 +603,7 @@ int swcu_destroy(swcu_ctx *c)
     for (auto &p : c->f4) cudaFree(p);
     for (auto &p : c->alt) cudaFree(p);
     cudaFree(c->mask); cudaFree(c->bad_dev);
+    cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev);
     if (c->bad_host) cudaFreeHost(c->bad_host);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
@@ -520,6 +619,17 @@ int swcu_upload(swcu_ctx *c, int field, const void *host) { return upload_impl(c
 int swcu_upload_from_device(swcu_ctx *c, int field, const void *dev) { return upload_impl(c, field, dev, true); }
 int swcu_download(swcu_ctx *c, int field, void *host) { return download_impl(c, field, host, false); }
 int swcu_download_to_device(swcu_ctx *c, int field, void *dev) { return download_impl(c, field, dev, true); }
+
+int swcu_set_option(swcu_ctx *c, const char *name, int value)
+{
+    if (!c || !name) { set_error("null argument"); return SWCU_ERR_ARG; }
+    if (!strcmp(name, "metric_tables")) { c->want_tables = value != 0; c->metrics_dirty = true; return SWCU_OK; }
+    if (!strcmp(name, "tiled")) { c->want_tiled = value != 0; return SWCU_OK; }
+    if (!strcmp(name, "tile_variant")) { c->tile_variant = value; c->tmaps.clear(); return SWCU_OK; }
+    set_error("unknown option %s", name);
+    return SWCU_ERR_ARG;
+}
+int swcu_uses_metric_tables(const swcu_ctx *c) { return c && c->use_tables ? 1 : 0; }
 
 int swcu_envoke_hh_init(swcu_ctx *c)
 {

@@ -3,10 +3,20 @@
 //
 // Every function follows one statement of the reference's Fortran (file:line cited) with
 // Fortran's evaluation rules: equal-precedence operators left to right, a binary operation in
-// the wider kind of its operands (float*float stays float), successive divisions are true
+// the wider kind of its operands (real(4)*real(4) stays real(4)), successive divisions are true
 // divisions.  This translation unit MUST be compiled with -fmad=false (and the default
 // -prec-div=true -ftz=false) so no multiply-add is contracted: the results are then bitwise
 // equal to a strict IEEE CPU evaluation.
+//
+// The reference's real(4) metric / Coriolis arrays enter through a "metric accessor" M that
+// returns each quantity ALREADY PROMOTED to double (promotion is exact, so where it happens does
+// not change a bit).  real(4) sub-expressions of the reference (dx*dy, dy**2, dy/dx, ...) are
+// separate accessor methods that evaluate in real(4) first.  Two accessors exist:
+//   MetGen  reads the real(4) 2-D arrays and converts per use (any grid; Level A and fallback);
+//   MetRow  reads per-row tables of doubles built once on the device (grids whose metrics depend
+//           on the row only: carthesian and unrotated spherical, i.e. every shipped setup).
+// MetRow exists because on B200 the F2F.F64.F32 conversion issues on the quarter-rate XU pipe:
+// ncu showed the converting kernel XU-bound (62 % XU, 26 % fp64, 25 % DRAM).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,175 +36,208 @@ __device__ __forceinline__ long ix(const Geo &g, int m, int n)
 
 __device__ __forceinline__ bool on(float mask) { return mask > 0.5f; }
 
+// ---- metric accessors -------------------------------------------------------------------------
+// c = flat index of the cell, r = its row (n - by1).  Neighbours: (m+-1) -> (c+-1, r),
+// (n+-1) -> (c+-p, r+-1).
+struct MetGen {
+    const float *dx_, *dy_, *dxt_, *dyt_, *dxh_, *dyh_, *dxb_, *dyb_, *rlh_;
+    __device__ __forceinline__ double dx(long c, int) const { return (double)dx_[c]; }
+    __device__ __forceinline__ double dy(long c, int) const { return (double)dy_[c]; }
+    __device__ __forceinline__ double dxt(long c, int) const { return (double)dxt_[c]; }
+    __device__ __forceinline__ double dyt(long c, int) const { return (double)dyt_[c]; }
+    __device__ __forceinline__ double dxh(long c, int) const { return (double)dxh_[c]; }
+    __device__ __forceinline__ double dyh(long c, int) const { return (double)dyh_[c]; }
+    __device__ __forceinline__ double dxb(long c, int) const { return (double)dxb_[c]; }
+    __device__ __forceinline__ double dyb(long c, int) const { return (double)dyb_[c]; }
+    __device__ __forceinline__ double rlh(long c, int) const { return (double)rlh_[c]; }
+    // real(4) sub-expressions of the reference
+    __device__ __forceinline__ double area(long c, int) const { return (double)(dx_[c] * dy_[c]); }    // dx*dy
+    __device__ __forceinline__ double dy2(long c, int) const { return (double)(dy_[c] * dy_[c]); }     // dy**2
+    __device__ __forceinline__ double dx2(long c, int) const { return (double)(dx_[c] * dx_[c]); }
+    __device__ __forceinline__ double dxb2(long c, int) const { return (double)(dxb_[c] * dxb_[c]); }
+    __device__ __forceinline__ double dyb2(long c, int) const { return (double)(dyb_[c] * dyb_[c]); }
+    __device__ __forceinline__ double ryx(long c, int) const { return (double)(dy_[c] / dx_[c]); }     // dy/dx
+    __device__ __forceinline__ double rxy(long c, int) const { return (double)(dx_[c] / dy_[c]); }     // dx/dy
+    __device__ __forceinline__ double rxyb(long c, int) const { return (double)(dxb_[c] / dyb_[c]); }  // dxb/dyb
+    __device__ __forceinline__ double ryxb(long c, int) const { return (double)(dyb_[c] / dxb_[c]); }  // dyb/dxb
+};
+
+enum MetTab : int {
+    T_DX, T_DY, T_DXT, T_DYT, T_DXH, T_DYH, T_DXB, T_DYB, T_RLH,
+    T_AREA, T_DY2, T_DX2, T_DXB2, T_DYB2, T_RYX, T_RXY, T_RXYB, T_RYXB, T_COUNT
+};
+
+struct MetRow {
+    const double *tab;  // [T_COUNT][h]
+    int h;
+#define SWCU_ROW(name, T) \
+    __device__ __forceinline__ double name(long, int r) const { return __ldg(tab + (T) * h + r); }
+    SWCU_ROW(dx, T_DX) SWCU_ROW(dy, T_DY) SWCU_ROW(dxt, T_DXT) SWCU_ROW(dyt, T_DYT)
+    SWCU_ROW(dxh, T_DXH) SWCU_ROW(dyh, T_DYH) SWCU_ROW(dxb, T_DXB) SWCU_ROW(dyb, T_DYB)
+    SWCU_ROW(rlh, T_RLH) SWCU_ROW(area, T_AREA) SWCU_ROW(dy2, T_DY2) SWCU_ROW(dx2, T_DX2)
+    SWCU_ROW(dxb2, T_DXB2) SWCU_ROW(dyb2, T_DYB2) SWCU_ROW(ryx, T_RYX) SWCU_ROW(rxy, T_RXY)
+    SWCU_ROW(rxyb, T_RXYB) SWCU_ROW(ryxb, T_RYXB)
+#undef SWCU_ROW
+};
+
+// ---- formulas -----------------------------------------------------------------------------------
+
 // kernel/shallow_water/vel_ssh.f90:98-100
-__device__ __forceinline__ double f_sshn(long c, int p, double tau,
-        const float *__restrict__ dx, const float *__restrict__ dy,
-        const float *__restrict__ dxh, const float *__restrict__ dyh,
+template <class M>
+__device__ __forceinline__ double f_sshn(long c, int r, int p, double tau, const M &m,
         const double *__restrict__ hhu, const double *__restrict__ hhv,
         const double *__restrict__ sshp, const double *__restrict__ u, const double *__restrict__ v)
 {
     const long w = c - 1, s = c - p;
-    const float area = dx[c] * dy[c];
-    const double div = u[c] * hhu[c] * dyh[c] - u[w] * hhu[w] * dyh[w]
-                     + v[c] * hhv[c] * dxh[c] - v[s] * hhv[s] * dxh[s];
-    return sshp[c] + 2.0 * tau * (-(div / area));
+    const double div = u[c] * hhu[c] * m.dyh(c, r) - u[w] * hhu[w] * m.dyh(w, r)
+                     + v[c] * hhv[c] * m.dxh(c, r) - v[s] * hhv[s] * m.dxh(s, r - 1);
+    return sshp[c] + 2.0 * tau * (-(div / m.area(c, r)));
 }
 
-// kernel/shallow_water/depth.f90:59-61 (and :70-72 with the +y neighbour)
+// kernel/shallow_water/depth.f90:59-61 (and :70-72 with the +y neighbour).  lu_* are the real(4)
+// masks promoted to double (their real(4) sum is exact, so summing the doubles gives the same slu).
 __device__ __forceinline__ double f_interp2(double hq_c, double hq_e,
-        float dx_c, float dy_c, float lu_c, float dx_e, float dy_e, float lu_e, float d1, float d2)
+        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e, double d1, double d2)
 {
-    const double slu = (double)(lu_c + lu_e);
-    return (hq_c * dx_c * dy_c * (double)lu_c + hq_e * dx_e * dy_e * (double)lu_e) / slu / d1 / d2;
+    const double slu = lu_c + lu_e;
+    return (hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e) / slu / d1 / d2;
 }
 
 // kernel/shallow_water/depth.f90:81-85
 __device__ __forceinline__ double f_interp4(double hq_c, double hq_e, double hq_n, double hq_en,
-        float dx_c, float dy_c, float lu_c, float dx_e, float dy_e, float lu_e,
-        float dx_n, float dy_n, float lu_n, float dx_en, float dy_en, float lu_en, float dxb, float dyb)
+        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e,
+        double dx_n, double dy_n, double lu_n, double dx_en, double dy_en, double lu_en, double dxb, double dyb)
 {
-    const double slu = (double)(lu_c + lu_e + lu_n + lu_en);
-    return (hq_c * dx_c * dy_c * (double)lu_c + hq_e * dx_e * dy_e * (double)lu_e
-          + hq_n * dx_n * dy_n * (double)lu_n + hq_en * dx_en * dy_en * (double)lu_en) / slu / dxb / dyb;
+    const double slu = lu_c + lu_e + lu_n + lu_en;
+    return (hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e
+          + hq_n * dx_n * dy_n * lu_n + hq_en * dx_en * dy_en * lu_en) / slu / dxb / dyb;
 }
 
 // kernel/shallow_water/vel_ssh.f90:273-275
-__device__ __forceinline__ double f_vort(long c, int p,
-        const float *__restrict__ dxt, const float *__restrict__ dyt,
-        const float *__restrict__ dxb, const float *__restrict__ dyb,
+template <class M>
+__device__ __forceinline__ double f_vort(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v)
 {
     const long e = c + 1, no = c + p;
-    return (v[e] * dyt[e] - v[c] * dyt[c])
-         - (u[no] * dxt[no] - u[c] * dxt[c])
-         - ((v[e] - v[c]) * dyb[c] - (u[no] - u[c]) * dxb[c]);
+    return (v[e] * m.dyt(e, r) - v[c] * m.dyt(c, r))
+         - (u[no] * m.dxt(no, r + 1) - u[c] * m.dxt(c, r))
+         - ((v[e] - v[c]) * m.dyb(c, r) - (u[no] - u[c]) * m.dxb(c, r));
 }
 
 // kernel/shallow_water/mixing.f90:43-44
-__device__ __forceinline__ double f_str_t(long c, int p,
-        const float *__restrict__ dx, const float *__restrict__ dy,
-        const float *__restrict__ dxh, const float *__restrict__ dyh,
+template <class M>
+__device__ __forceinline__ double f_str_t(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v)
 {
     const long w = c - 1, s = c - p;
-    const float ryx = dy[c] / dx[c], rxy = dx[c] / dy[c];
-    return ryx * (u[c] / dyh[c] - u[w] / dyh[w]) - rxy * (v[c] / dxh[c] - v[s] / dxh[s]);
+    return m.ryx(c, r) * (u[c] / m.dyh(c, r) - u[w] / m.dyh(w, r))
+         - m.rxy(c, r) * (v[c] / m.dxh(c, r) - v[s] / m.dxh(s, r - 1));
 }
 
 // kernel/shallow_water/mixing.f90:50-51
-__device__ __forceinline__ double f_str_s(long c, int p,
-        const float *__restrict__ dxt, const float *__restrict__ dyt,
-        const float *__restrict__ dxb, const float *__restrict__ dyb,
+template <class M>
+__device__ __forceinline__ double f_str_s(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v)
 {
     const long e = c + 1, no = c + p;
-    const float rxy = dxb[c] / dyb[c], ryx = dyb[c] / dxb[c];
-    return rxy * (u[no] / dxt[no] - u[c] / dxt[c]) + ryx * (v[e] / dyt[e] - v[c] / dyt[c]);
+    return m.rxyb(c, r) * (u[no] / m.dxt(no, r + 1) - u[c] / m.dxt(c, r))
+         + m.ryxb(c, r) * (v[e] / m.dyt(e, r) - v[c] / m.dyt(c, r));
 }
 
-// kernel/shallow_water/vel_ssh.f90:326-340
-__device__ __forceinline__ double f_rhsx_adv(long c, int p, float luu_c, float luu_s,
-        const float *__restrict__ dxh, const float *__restrict__ dyh,
+// kernel/shallow_water/vel_ssh.f90:326-340 ; luu_c / luu_s = dble(luu(m,n)) / dble(luu(m,n-1))
+template <class M>
+__device__ __forceinline__ double f_rhsx_adv(long c, int r, int p, const M &m, double luu_c, double luu_s,
         const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ vort,
         const double *__restrict__ hu, const double *__restrict__ hv, const double *__restrict__ hh)
 {
     const long e = c + 1, w = c - 1, no = c + p, s = c - p, es = c + 1 - p;
-    const double fx_p = (u[c] * dyh[c] * hu[c] + u[e] * dyh[e] * hu[e]) / 2.0 * (u[c] + u[e]) / 2.0;
-    const double fx_m = (u[c] * dyh[c] * hu[c] + u[w] * dyh[w] * hu[w]) / 2.0 * (u[c] + u[w]) / 2.0;
-    const double fy_p = (v[c] * dxh[c] * hv[c] + v[e] * dxh[e] * hv[e]) / 2.0 * (u[no] + u[c]) / 2.0 * (double)luu_c;
-    const double fy_m = (v[s] * dxh[s] * hv[s] + v[es] * dxh[es] * hv[es]) / 2.0 * (u[s] + u[c]) / 2.0 * (double)luu_s;
+    const double fx_p = (u[c] * m.dyh(c, r) * hu[c] + u[e] * m.dyh(e, r) * hu[e]) / 2.0 * (u[c] + u[e]) / 2.0;
+    const double fx_m = (u[c] * m.dyh(c, r) * hu[c] + u[w] * m.dyh(w, r) * hu[w]) / 2.0 * (u[c] + u[w]) / 2.0;
+    const double fy_p = (v[c] * m.dxh(c, r) * hv[c] + v[e] * m.dxh(e, r) * hv[e]) / 2.0 * (u[no] + u[c]) / 2.0 * luu_c;
+    const double fy_m = (v[s] * m.dxh(s, r - 1) * hv[s] + v[es] * m.dxh(es, r - 1) * hv[es]) / 2.0 * (u[s] + u[c]) / 2.0 * luu_s;
     return -(fx_p - fx_m + fy_p - fy_m)
          + (vort[c] * hh[c] * (v[e] + v[c]) + vort[s] * hh[s] * (v[es] + v[s])) / 4.0;
 }
 
 // kernel/shallow_water/vel_ssh.f90:351-365
-__device__ __forceinline__ double f_rhsy_adv(long c, int p,
-        const float *__restrict__ dxh, const float *__restrict__ dyh,
+template <class M>
+__device__ __forceinline__ double f_rhsy_adv(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ vort,
         const double *__restrict__ hu, const double *__restrict__ hv, const double *__restrict__ hh)
 {
     const long e = c + 1, w = c - 1, no = c + p, s = c - p, wn = c - 1 + p;
-    const double fy_p = (v[c] * dxh[c] * hv[c] + v[no] * dxh[no] * hv[no]) / 2.0 * (v[c] + v[no]) / 2.0;
-    const double fy_m = (v[c] * dxh[c] * hv[c] + v[s] * dxh[s] * hv[s]) / 2.0 * (v[c] + v[s]) / 2.0;
-    const double fx_p = (u[c] * dyh[c] * hu[c] + u[no] * dyh[no] * hu[no]) / 2.0 * (v[e] + v[c]) / 2.0;
-    const double fx_m = (u[w] * dyh[w] * hu[w] + u[wn] * dyh[wn] * hu[wn]) / 2.0 * (v[w] + v[c]) / 2.0;
+    const double fy_p = (v[c] * m.dxh(c, r) * hv[c] + v[no] * m.dxh(no, r + 1) * hv[no]) / 2.0 * (v[c] + v[no]) / 2.0;
+    const double fy_m = (v[c] * m.dxh(c, r) * hv[c] + v[s] * m.dxh(s, r - 1) * hv[s]) / 2.0 * (v[c] + v[s]) / 2.0;
+    const double fx_p = (u[c] * m.dyh(c, r) * hu[c] + u[no] * m.dyh(no, r + 1) * hu[no]) / 2.0 * (v[e] + v[c]) / 2.0;
+    const double fx_m = (u[w] * m.dyh(w, r) * hu[w] + u[wn] * m.dyh(wn, r + 1) * hu[wn]) / 2.0 * (v[w] + v[c]) / 2.0;
     return -(fx_p - fx_m + fy_p - fy_m)
          - (vort[c] * hh[c] * (u[no] + u[c]) + vort[w] * hh[w] * (u[wn] + u[w])) / 4.0;
 }
 
 // kernel/shallow_water/vel_ssh.f90:422-428 ; hq_c / hq_e are hq(m,n) / hq(m+1,n)
-__device__ __forceinline__ double f_rhsx_dif(long c, int p, double hq_c, double hq_e,
-        const float *__restrict__ dy, const float *__restrict__ dxt, const float *__restrict__ dyh,
-        const float *__restrict__ dxb,
+template <class M>
+__device__ __forceinline__ double f_rhsx_dif(long c, int r, int p, const M &m, double hq_c, double hq_e,
         const double *__restrict__ mu, const double *__restrict__ str_t, const double *__restrict__ str_s,
         const double *__restrict__ hh)
 {
     const long e = c + 1, no = c + p, s = c - p, en = c + 1 + p, es = c + 1 - p;
     const double muh_p = (mu[c] + mu[e] + mu[no] + mu[en]) / 4.0;
     const double muh_m = (mu[c] + mu[e] + mu[s] + mu[es]) / 4.0;
-    const float dy2e = dy[e] * dy[e], dy2c = dy[c] * dy[c];
-    const float dxb2c = dxb[c] * dxb[c], dxb2s = dxb[s] * dxb[s];
-    return (dy2e * mu[e] * hq_e * str_t[e] - dy2c * mu[c] * hq_c * str_t[c]) / dyh[c]
-         + (dxb2c * muh_p * hh[c] * str_s[c] - dxb2s * muh_m * hh[s] * str_s[s]) / dxt[c];
+    return (m.dy2(e, r) * mu[e] * hq_e * str_t[e] - m.dy2(c, r) * mu[c] * hq_c * str_t[c]) / m.dyh(c, r)
+         + (m.dxb2(c, r) * muh_p * hh[c] * str_s[c] - m.dxb2(s, r - 1) * muh_m * hh[s] * str_s[s]) / m.dxt(c, r);
 }
 
 // kernel/shallow_water/vel_ssh.f90:438-444 ; hq_c / hq_n are hq(m,n) / hq(m,n+1)
-__device__ __forceinline__ double f_rhsy_dif(long c, int p, double hq_c, double hq_n,
-        const float *__restrict__ dx, const float *__restrict__ dyt, const float *__restrict__ dxh,
-        const float *__restrict__ dyb,
+template <class M>
+__device__ __forceinline__ double f_rhsy_dif(long c, int r, int p, const M &m, double hq_c, double hq_n,
         const double *__restrict__ mu, const double *__restrict__ str_t, const double *__restrict__ str_s,
         const double *__restrict__ hh)
 {
     const long e = c + 1, w = c - 1, no = c + p, en = c + 1 + p, wn = c - 1 + p;
     const double muh_p = (mu[c] + mu[e] + mu[no] + mu[en]) / 4.0;
     const double muh_m = (mu[c] + mu[w] + mu[no] + mu[wn]) / 4.0;
-    const float dx2n = dx[no] * dx[no], dx2c = dx[c] * dx[c];
-    const float dyb2c = dyb[c] * dyb[c], dyb2w = dyb[w] * dyb[w];
-    return -(dx2n * mu[no] * hq_n * str_t[no] - dx2c * mu[c] * hq_c * str_t[c]) / dxh[c]
-         + (dyb2c * muh_p * hh[c] * str_s[c] - dyb2w * muh_m * hh[w] * str_s[w]) / dyt[c];
+    return -(m.dx2(no, r + 1) * mu[no] * hq_n * str_t[no] - m.dx2(c, r) * mu[c] * hq_c * str_t[c]) / m.dxh(c, r)
+         + (m.dyb2(c, r) * muh_p * hh[c] * str_s[c] - m.dyb2(w, r) * muh_m * hh[w] * str_s[w]) / m.dyt(c, r);
 }
 
-// kernel/shallow_water/vel_ssh.f90:167-176 ; FreeFallAcc is real(4) 9.8 promoted
-__device__ __forceinline__ double f_un(long c, int p, double tau,
-        double hu_c, double hun_c, double hup_c, double rhsx, double rhsx_dif, double rhsx_adv,
-        float rd /* rdis(m,n)+rdis(m+1,n), a real(4) sum */,
-        const float *__restrict__ dxt, const float *__restrict__ dyh,
-        const float *__restrict__ dxb, const float *__restrict__ dyb,
-        const float *__restrict__ rlh_s,
+// kernel/shallow_water/vel_ssh.f90:167-176 ; FreeFallAcc is real(4) 9.8 promoted;
+// rd = dble(rdis(m,n)+rdis(m+1,n)), the real(4) sum promoted
+template <class M>
+__device__ __forceinline__ double f_un(long c, int r, int p, double tau, const M &m,
+        double hu_c, double hun_c, double hup_c, double rhsx, double rhsx_dif, double rhsx_adv, double rd,
         const double *__restrict__ hhh, const double *__restrict__ ssh,
         const double *__restrict__ v, const double *__restrict__ up)
 {
     const long e = c + 1, s = c - p, es = c + 1 - p;
     const double g = (double)9.8f;
-    const double bp = hun_c * dxt[c] * dyh[c] / 2.0 / tau;
-    const double bp0 = hup_c * dxt[c] * dyh[c] / 2.0 / tau;
-    const double slx = -g * (ssh[e] - ssh[c]) * dyh[c] * hu_c;
+    const double dxt = m.dxt(c, r), dyh = m.dyh(c, r);
+    const double bp = hun_c * dxt * dyh / 2.0 / tau;
+    const double bp0 = hup_c * dxt * dyh / 2.0 / tau;
+    const double slx = -g * (ssh[e] - ssh[c]) * dyh * hu_c;
     const double grx = rhsx + slx + rhsx_dif + rhsx_adv
-                     - rd / 2.0 * up[c] * dxt[c] * dyh[c] * hu_c
-                     + (rlh_s[c] * hhh[c] * dxb[c] * dyb[c] * (v[e] + v[c])
-                      + rlh_s[s] * hhh[s] * dxb[s] * dyb[s] * (v[es] + v[s])) / 4.0;
+                     - rd / 2.0 * up[c] * dxt * dyh * hu_c
+                     + (m.rlh(c, r) * hhh[c] * m.dxb(c, r) * m.dyb(c, r) * (v[e] + v[c])
+                      + m.rlh(s, r - 1) * hhh[s] * m.dxb(s, r - 1) * m.dyb(s, r - 1) * (v[es] + v[s])) / 4.0;
     return (up[c] * bp0 + grx) / bp;
 }
 
-// kernel/shallow_water/vel_ssh.f90:181-190
-__device__ __forceinline__ double f_vn(long c, int p, double tau,
-        double hv_c, double hvn_c, double hvp_c, double rhsy, double rhsy_dif, double rhsy_adv,
-        float rd /* rdis(m,n)+rdis(m,n+1), a real(4) sum */,
-        const float *__restrict__ dyt, const float *__restrict__ dxh,
-        const float *__restrict__ dxb, const float *__restrict__ dyb,
-        const float *__restrict__ rlh_s,
+// kernel/shallow_water/vel_ssh.f90:181-190 ; rd = dble(rdis(m,n)+rdis(m,n+1))
+template <class M>
+__device__ __forceinline__ double f_vn(long c, int r, int p, double tau, const M &m,
+        double hv_c, double hvn_c, double hvp_c, double rhsy, double rhsy_dif, double rhsy_adv, double rd,
         const double *__restrict__ hhh, const double *__restrict__ ssh,
         const double *__restrict__ u, const double *__restrict__ vp)
 {
     const long w = c - 1, no = c + p, wn = c - 1 + p;
     const double g = (double)9.8f;
-    const double bp = hvn_c * dyt[c] * dxh[c] / 2.0 / tau;
-    const double bp0 = hvp_c * dyt[c] * dxh[c] / 2.0 / tau;
-    const double sly = -g * (ssh[no] - ssh[c]) * dxh[c] * hv_c;
+    const double dyt = m.dyt(c, r), dxh = m.dxh(c, r);
+    const double bp = hvn_c * dyt * dxh / 2.0 / tau;
+    const double bp0 = hvp_c * dyt * dxh / 2.0 / tau;
+    const double sly = -g * (ssh[no] - ssh[c]) * dxh * hv_c;
     const double gry = rhsy + sly + rhsy_dif + rhsy_adv
-                     - rd / 2.0 * vp[c] * dxh[c] * dyt[c] * hv_c
-                     - (rlh_s[c] * hhh[c] * dxb[c] * dyb[c] * (u[no] + u[c])
-                      + rlh_s[w] * hhh[w] * dxb[w] * dyb[w] * (u[wn] + u[w])) / 4.0;
+                     - rd / 2.0 * vp[c] * dxh * dyt * hv_c
+                     - (m.rlh(c, r) * hhh[c] * m.dxb(c, r) * m.dyb(c, r) * (u[no] + u[c])
+                      + m.rlh(w, r) * hhh[w] * m.dxb(w, r) * m.dyb(w, r) * (u[wn] + u[w])) / 4.0;
     return (vp[c] * bp0 + gry) / bp;
 }
 

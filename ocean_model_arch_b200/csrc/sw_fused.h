@@ -1,11 +1,14 @@
 // sw_fused.h -- argument block and launchers of the fused Level-B kernels (sw_kernels_fused.cu)
 #pragma once
+#include <cuda.h>
+
+#include "sw_cells.cuh"
 #include "sw_common.h"
 
 namespace swcu {
 
-// bit <=> the reference's real(4) mask of the same name is > 0.5 (core/grid.f90:24-31)
-enum : int { MB_LU = 1, MB_LCU = 2, MB_LCV = 4, MB_LUU = 8, MB_LUH = 16, MB_LLU = 32, MB_LLV = 64 };
+// TMA descriptors of the eight arrays the tiled kernel loads: ssh, sshp, u, up, v, vp, hhq_rest, mu
+struct StepMaps { CUtensorMap m[8]; };
 
 struct FusedArgs {
     // time-level-n state (read) and n+1 state (written): ping-pong buffers
@@ -19,6 +22,8 @@ struct FusedArgs {
     // static real(4)
     const float *dx, *dy, *dxt, *dyt, *dxh, *dyh, *dxb, *dyb, *rlh_s;
     const float *rdis;  // nullptr <=> identically zero
+    const double *tab;  // per-row metric tables [T_COUNT][tab_h], nullptr <=> use the 2-D real(4) arrays
+    int tab_h;
     const unsigned char *mask;
     int *bad;  // K11 counter
     double tau, ts, ffs;
@@ -28,6 +33,15 @@ struct FusedArgs {
 // prep on rows [n0..n1] (columns nx_start-1 .. nx_end+1); update on rows [n0..n1] (columns of S)
 int launch_prep(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);
 int launch_update(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);
+// the whole step for rows [n0..n1] in ONE launch (TMA-staged shared-memory tiles); needs a.tab
+int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, int variant,
+                      cudaStream_t st);
+bool step_tiled_supported(const FusedArgs &a);
+void step_tile_box(int variant, int *box_w, int *box_h);
+// Builds the per-row tables from column nx_start of the nine real(4) arrays and counts (into
+// *nonrow_dev) the cells whose values differ from their row's entry.
+int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, int *nonrow_dev,
+                        const float *const *arr_list_dev, cudaStream_t st);
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 

@@ -15,6 +15,8 @@
 //   - every depth field is a pure function of (hhq_rest, ssh, sshp, masks, metrics).
 // Masks arrive packed one byte per cell (bit set <=> reference mask > 0.5); stores are selects,
 // never multiplications by the mask (masked lanes may hold Inf/NaN).
+// Metrics come through an accessor (sw_formulas.cuh): MetRow (per-row double tables, no
+// conversions, no HBM traffic) when every metric array is constant along m, else MetGen.
 // Arithmetic is the shared sw_formulas.cuh, so results are bitwise those of the 1:1 kernels.
 #include "sw_fused.h"
 
@@ -25,43 +27,35 @@ namespace {
 constexpr int BX = 64;
 constexpr int BY = 4;
 
-__device__ __forceinline__ float mf(unsigned char bits, int bit) { return (bits & bit) ? 1.0f : 0.0f; }
+template <bool ROW> struct MetOf;
+template <> struct MetOf<true> {
+    typedef MetRow type;
+    static __device__ __forceinline__ MetRow make(const FusedArgs &a) { return MetRow{a.tab, a.tab_h}; }
+};
+template <> struct MetOf<false> {
+    typedef MetGen type;
+    static __device__ __forceinline__ MetGen make(const FusedArgs &a)
+    {
+        return MetGen{a.dx, a.dy, a.dxt, a.dyt, a.dxh, a.dyh, a.dxb, a.dyb, a.rlh_s};
+    }
+};
 
-template <bool TRANS, bool LAT>
+// ---- two-launch path: stages A and B straight from global memory (any metric arrays) ----------
+template <bool ROW, bool TRANS, bool LAT>
 __global__ void __launch_bounds__(BX *BY) k_prep(Geo g, FusedArgs a, int n0, int n1)
 {
     const int m = g.nx_start - 1 + blockIdx.x * BX + threadIdx.x;
     const int n = n0 + blockIdx.y * BY + threadIdx.y;
     if (m > g.nx_end + 1 || n > n1) return;
     const long c = ix(g, m, n);
-    const int p = g.pitch;
-    const long e = c + 1, no = c + p, en = c + 1 + p;
-    const unsigned char mb = a.mask[c];
-    const double ffs = a.ffs;
-
-    // K10: depth.f90:48, 57-94 (hq = h_r + sh*ffs re-evaluated per neighbour)
-    const double q_c = a.h_r[c] + a.ssh[c] * ffs, q_e = a.h_r[e] + a.ssh[e] * ffs;
-    const double q_n = a.h_r[no] + a.ssh[no] * ffs, q_en = a.h_r[en] + a.ssh[en] * ffs;
-    const float lu_c = mf(mb, MB_LU), lu_e = mf(a.mask[e], MB_LU);
-    const float lu_n = mf(a.mask[no], MB_LU), lu_en = mf(a.mask[en], MB_LU);
-    const float dx_c = a.dx[c], dy_c = a.dy[c], dx_e = a.dx[e], dy_e = a.dy[e];
-    const float dx_n = a.dx[no], dy_n = a.dy[no], dx_en = a.dx[en], dy_en = a.dy[en];
-    double hu = 0.0, hv = 0.0, hh = 0.0;
-    if (mb & MB_LLU) hu = f_interp2(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, a.dxt[c], a.dyh[c]);
-    if (mb & MB_LLV) hv = f_interp2(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, a.dxh[c], a.dyt[c]);
-    if (mb & MB_LUH)
-        hh = f_interp4(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
-                       dx_en, dy_en, lu_en, a.dxb[c], a.dyb[c]);
-    a.hu[c] = hu; a.hv[c] = hv; a.hh[c] = hh;
-
-    if (TRANS) a.vort[c] = (mb & MB_LUU) ? f_vort(c, p, a.dxt, a.dyt, a.dxb, a.dyb, a.u, a.v) : 0.0;
-    if (LAT) {
-        a.str_t[c] = (mb & MB_LU) ? f_str_t(c, p, a.dx, a.dy, a.dxh, a.dyh, a.up, a.vp) : 0.0;
-        a.str_s[c] = (mb & MB_LUU) ? f_str_s(c, p, a.dxt, a.dyt, a.dxb, a.dyb, a.up, a.vp) : 0.0;
-    }
+    const typename MetOf<ROW>::type mt = MetOf<ROW>::make(a);
+    const PrepOut o = prep_cell<TRANS, LAT>(c, n - g.by1, g.pitch, mt, a.ffs, a.mask, a.ssh, a.h_r, a.u, a.v, a.up, a.vp);
+    a.hu[c] = o.hu; a.hv[c] = o.hv; a.hh[c] = o.hh;
+    if (TRANS) a.vort[c] = o.vort;
+    if (LAT) { a.str_t[c] = o.str_t; a.str_s[c] = o.str_s; }
 }
 
-template <bool TRANS, bool LAT, bool HAS_RHS, bool HAS_RDISS>
+template <bool ROW, bool TRANS, bool LAT, bool HAS_RHS, bool HAS_RDISS>
 __global__ void __launch_bounds__(BX *BY) k_update(Geo g, FusedArgs a, int n0, int n1)
 {
     const int m = g.nx_start + blockIdx.x * BX + threadIdx.x;
@@ -69,61 +63,148 @@ __global__ void __launch_bounds__(BX *BY) k_update(Geo g, FusedArgs a, int n0, i
     if (m > g.nx_end || n > n1) return;
     const long c = ix(g, m, n);
     const int p = g.pitch;
-    const long e = c + 1, no = c + p;
-    const unsigned char mb = a.mask[c];
-    const double tau = a.tau, ts = a.ts, ffs = a.ffs;
+    const typename MetOf<ROW>::type mt = MetOf<ROW>::make(a);
+    const double rhsx = HAS_RHS ? a.RHSx[c] : 0.0, rhsy = HAS_RHS ? a.RHSy[c] : 0.0;
+    const double rdx = HAS_RDISS ? (double)(a.rdis[c] + a.rdis[c + 1]) : 0.0;
+    const double rdy = HAS_RDISS ? (double)(a.rdis[c] + a.rdis[c + p]) : 0.0;
+    const UpdOut o = update_cell<TRANS, LAT>(c, n - g.by1, p, mt, a.tau, a.ts, a.ffs, a.mask, a.ssh, a.sshp, a.u, a.up,
+                                             a.v, a.vp, a.h_r, a.mu, a.hu, a.hv, a.hh, a.vort, a.str_t, a.str_s,
+                                             rhsx, rhsy, rdx, rdy);
+    a.ssh_o[c] = o.ssh; a.sshp_o[c] = o.sshp; a.u_o[c] = o.u; a.up_o[c] = o.up; a.v_o[c] = o.v; a.vp_o[c] = o.vp;
+    if (o.bad) atomicAdd(a.bad, 1);  // K11
+}
 
-    const double ssh_c = a.ssh[c], sshp_c = a.sshp[c];
-    const double u_c = a.u[c], up_c = a.up[c], v_c = a.v[c], vp_c = a.vp[c];
+// ---- one-launch path: TMA-staged shared-memory tiles, stages A and B in one kernel --------------
+// A CTA owns TX x TY output cells.  One thread issues eight cp.async.bulk.tensor.2d loads (ssh,
+// sshp, u, up, v, vp, hhq_rest, mu; box = tile + 2-cell halo, out-of-array cells zero-filled) that
+// complete on one mbarrier; stage A then fills the six intermediate tiles for the tile grown by one
+// cell, stage B updates the tile and stores the six n+1 arrays.  Nothing but the prognostic state
+// touches HBM: 8 reads + 6 writes + 1 mask byte = 113 B per cell instead of 326 B.
+constexpr int TX = 32, HALO = 2, IW = TX + 2 * HALO;   // 36 columns per tile row
+constexpr int N_IN = 8, N_S1 = 6;
 
-    // K1
-    double ssh_new = ssh_c, sshp_new = sshp_c;
-    if (mb & MB_LU) {
-        const double sshn = f_sshn(c, p, tau, a.dx, a.dy, a.dxh, a.dyh, a.hu, a.hv, a.sshp, a.u, a.v);
-        sshp_new = f_filter(ssh_c, sshn, sshp_c, ts);  // K8, vel_ssh.f90:230-231
-        ssh_new = sshn;
-        if (!(sshn < 10000.0 && sshn > -10000.0)) atomicAdd(a.bad, 1);  // K11, vel_ssh.f90:55
+// tile variants: TY_ rows per tile, R_ vertically adjacent cells per thread in stage B, MINB_ CTAs per SM
+template <int TY_, int R_, int MINB_> struct TileCfg {
+    static constexpr int TY = TY_, R = R_, MINB = MINB_;
+    static constexpr int IH = TY + 2 * HALO, TILE = IW * IH;
+    static constexpr int THREADS = TX * TY / R;
+    static constexpr int MASK_BYTES = (TILE + 127) / 128 * 128;
+    static constexpr size_t SMEM = (size_t)(N_IN + N_S1) * TILE * sizeof(double) + MASK_BYTES + 16;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <class CFG, bool TRANS, bool LAT, bool HAS_RHS, bool HAS_RDISS>
+__global__ void __launch_bounds__(CFG::THREADS, CFG::MINB)
+k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1)
+{
+    constexpr int TY = CFG::TY, R = CFG::R, IH = CFG::IH, TILE = CFG::TILE, THREADS = CFG::THREADS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double *in = reinterpret_cast<double *>(smem_raw);
+    double *s1 = in + N_IN * TILE;
+    unsigned char *mk = reinterpret_cast<unsigned char *>(s1 + N_S1 * TILE);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(mk + CFG::MASK_BYTES);
+
+    const int tid = threadIdx.x;
+    const int i0 = g.nx_start + blockIdx.x * TX, j0 = n0 + blockIdx.y * TY;
+    const int ax = i0 - HALO - g.bx1, ay = j0 - HALO - g.by1;  // tile origin in array coordinates (>= 0)
+    const int w = g.bx2 - g.bx1 + 1, h = g.by2 - g.by1 + 1;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    a.ssh_o[c] = ssh_new; a.sshp_o[c] = sshp_new;
-
-    double u_new = u_c, up_new = up_c, v_new = v_c, vp_new = vp_c;
-    if (mb & (MB_LCU | MB_LCV)) {
-        const double h_c = a.h_r[c];
-        const double q_c = h_c + ssh_c * ffs, qp_c = h_c + sshp_c * ffs;
-        const float dx_c = a.dx[c], dy_c = a.dy[c];
-        const float lu_c = mf(mb, MB_LU);
-        if (mb & MB_LCU) {
-            const double h_e = a.h_r[e];
-            const double q_e = h_e + a.ssh[e] * ffs, qp_e = h_e + a.sshp[e] * ffs;
-            const double hu_c = a.hu[c];
-            const double hup_c = f_interp2(qp_c, qp_e, dx_c, dy_c, lu_c, a.dx[e], a.dy[e], mf(a.mask[e], MB_LU),
-                                           a.dxt[c], a.dyh[c]);  // K10 with shp, depth.f90:62-63
-            const double adv = TRANS ? f_rhsx_adv(c, p, mf(mb, MB_LUU), mf(a.mask[c - p], MB_LUU), a.dxh, a.dyh, a.u, a.v, a.vort, a.hu, a.hv, a.hh) : 0.0;
-            const double dif = LAT ? f_rhsx_dif(c, p, q_c, q_e, a.dy, a.dxt, a.dyh, a.dxb, a.mu, a.str_t, a.str_s, a.hh) : 0.0;
-            const double rhs = HAS_RHS ? a.RHSx[c] : 0.0;
-            const float rd = HAS_RDISS ? a.rdis[c] + a.rdis[e] : 0.0f + 0.0f;
-            const double un = f_un(c, p, tau, hu_c, hu_c, hup_c, rhs, dif, adv, rd, a.dxt, a.dyh, a.dxb, a.dyb,
-                                   a.rlh_s, a.hh, a.ssh, a.v, a.up);
-            up_new = f_filter(u_c, un, up_c, ts);
-            u_new = un;
-        }
-        if (mb & MB_LCV) {
-            const double h_n = a.h_r[no];
-            const double q_n = h_n + a.ssh[no] * ffs, qp_n = h_n + a.sshp[no] * ffs;
-            const double hv_c = a.hv[c];
-            const double hvp_c = f_interp2(qp_c, qp_n, dx_c, dy_c, lu_c, a.dx[no], a.dy[no], mf(a.mask[no], MB_LU),
-                                           a.dxh[c], a.dyt[c]);  // depth.f90:73-74
-            const double adv = TRANS ? f_rhsy_adv(c, p, a.dxh, a.dyh, a.u, a.v, a.vort, a.hu, a.hv, a.hh) : 0.0;
-            const double dif = LAT ? f_rhsy_dif(c, p, q_c, q_n, a.dx, a.dyt, a.dxh, a.dyb, a.mu, a.str_t, a.str_s, a.hh) : 0.0;
-            const double rhs = HAS_RHS ? a.RHSy[c] : 0.0;
-            const float rd = HAS_RDISS ? a.rdis[c] + a.rdis[no] : 0.0f + 0.0f;
-            const double vn = f_vn(c, p, tau, hv_c, hv_c, hvp_c, rhs, dif, adv, rd, a.dyt, a.dxh, a.dxb, a.dyb,
-                                   a.rlh_s, a.hh, a.ssh, a.u, a.vp);
-            vp_new = f_filter(v_c, vn, vp_c, ts);
-            v_new = vn;
-        }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                     "r"((unsigned)(N_IN * TILE * sizeof(double))) : "memory");
+#pragma unroll
+        for (int k = 0; k < N_IN; ++k)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_u32(in + k * TILE)), "l"(reinterpret_cast<unsigned long long>(&maps.m[k])),
+                         "r"(ax), "r"(ay), "r"(smem_u32(bar)) : "memory");
     }
-    a.u_o[c] = u_new; a.up_o[c] = up_new; a.v_o[c] = v_new; a.vp_o[c] = vp_new;
+    for (int idx = tid; idx < TILE; idx += THREADS) {  // mask bytes: plain loads
+        const int lx = idx % IW, ly = idx / IW, gx = ax + lx, gy = ay + ly;
+        mk[idx] = (gx < w && gy < h) ? a.mask[(long)gy * g.pitch + gx] : (unsigned char)0;
+    }
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(0) : "memory");
+    }
+    __syncthreads();
+
+    const double *ssh = in, *sshp = in + TILE, *u = in + 2 * TILE, *up = in + 3 * TILE, *v = in + 4 * TILE,
+                 *vp = in + 5 * TILE, *h_r = in + 6 * TILE, *mu = in + 7 * TILE;
+    double *hu = s1, *hv = s1 + TILE, *hh = s1 + 2 * TILE, *vort = s1 + 3 * TILE, *str_t = s1 + 4 * TILE,
+           *str_s = s1 + 5 * TILE;
+    const MetRow mt{a.tab, a.tab_h};
+
+    // stage A on the tile grown by one cell: local columns 1..TX+2, rows 1..TY+2
+    constexpr int AW = TX + 2, AH = TY + 2;
+    for (int idx = tid; idx < AW * AH; idx += THREADS) {
+        const int lx = 1 + idx % AW, ly = 1 + idx / AW;
+        const int c = ly * IW + lx;
+        const PrepOut o = prep_cell<TRANS, LAT>(c, ay + ly, IW, mt, a.ffs, mk, ssh, h_r, u, v, up, vp);
+        hu[c] = o.hu; hv[c] = o.hv; hh[c] = o.hh; vort[c] = o.vort; str_t[c] = o.str_t; str_s[c] = o.str_s;
+    }
+    __syncthreads();
+
+    // stage B: thread (tx, ty) updates the R vertically adjacent cells (tx, R*ty .. R*ty+R-1), so the
+    // compiler shares their common neighbour loads and sub-expressions
+    const int tx = tid & (TX - 1), ty = tid / TX;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int lx = HALO + tx, ly = HALO + ty * R + k;
+        const int m = i0 + tx, n = j0 + ty * R + k;
+        if (m > g.nx_end || n > n1) continue;
+        const int c = ly * IW + lx;
+        const long gc = ix(g, m, n);
+        const double rhsx = HAS_RHS ? a.RHSx[gc] : 0.0, rhsy = HAS_RHS ? a.RHSy[gc] : 0.0;
+        const double rdx = HAS_RDISS ? (double)(a.rdis[gc] + a.rdis[gc + 1]) : 0.0;
+        const double rdy = HAS_RDISS ? (double)(a.rdis[gc] + a.rdis[gc + g.pitch]) : 0.0;
+        const UpdOut o = update_cell<TRANS, LAT>(c, ay + ly, IW, mt, a.tau, a.ts, a.ffs, mk, ssh, sshp, u, up, v, vp, h_r, mu,
+                                                 hu, hv, hh, vort, str_t, str_s, rhsx, rhsy, rdx, rdy);
+        a.ssh_o[gc] = o.ssh; a.sshp_o[gc] = o.sshp; a.u_o[gc] = o.u; a.up_o[gc] = o.up; a.v_o[gc] = o.v; a.vp_o[gc] = o.vp;
+        if (o.bad) atomicAdd(a.bad, 1);  // K11
+    }
+}
+
+inline int launched(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
+}
+
+template <bool ROW>
+void prep_dispatch(const Geo &g, const FusedArgs &a, int n0, int n1, dim3 grid, dim3 block, cudaStream_t st)
+{
+    if (a.trans && a.lat) k_prep<ROW, true, true><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else if (a.trans) k_prep<ROW, true, false><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else if (a.lat) k_prep<ROW, false, true><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else k_prep<ROW, false, false><<<grid, block, 0, st>>>(g, a, n0, n1);
+}
+
+template <bool ROW, bool T, bool L>
+void update_dispatch2(const Geo &g, const FusedArgs &a, int n0, int n1, dim3 grid, dim3 block, cudaStream_t st)
+{
+    const bool r = a.RHSx != nullptr, d = a.rdis != nullptr;
+    if (r && d) k_update<ROW, T, L, true, true><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else if (r) k_update<ROW, T, L, true, false><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else if (d) k_update<ROW, T, L, false, true><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else k_update<ROW, T, L, false, false><<<grid, block, 0, st>>>(g, a, n0, n1);
+}
+
+template <bool ROW>
+void update_dispatch(const Geo &g, const FusedArgs &a, int n0, int n1, dim3 grid, dim3 block, cudaStream_t st)
+{
+    if (a.trans && a.lat) update_dispatch2<ROW, true, true>(g, a, n0, n1, grid, block, st);
+    else if (a.trans) update_dispatch2<ROW, true, false>(g, a, n0, n1, grid, block, st);
+    else if (a.lat) update_dispatch2<ROW, false, true>(g, a, n0, n1, grid, block, st);
+    else update_dispatch2<ROW, false, false>(g, a, n0, n1, grid, block, st);
 }
 
 }  // namespace
@@ -133,22 +214,9 @@ int launch_prep(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t s
     if (n1 < n0) return SWCU_OK;
     const dim3 block(BX, BY, 1);
     const dim3 grid((unsigned)((g.nx_end - g.nx_start + 2 + BX) / BX), (unsigned)((n1 - n0 + BY) / BY), 1);
-    if (a.trans && a.lat) k_prep<true, true><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else if (a.trans) k_prep<true, false><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else if (a.lat) k_prep<false, true><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else k_prep<false, false><<<grid, block, 0, st>>>(g, a, n0, n1);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, "prep");
-}
-
-template <bool T, bool L>
-static void update_dispatch(const Geo &g, const FusedArgs &a, int n0, int n1, dim3 grid, dim3 block, cudaStream_t st)
-{
-    const bool r = a.RHSx != nullptr, d = a.rdis != nullptr;
-    if (r && d) k_update<T, L, true, true><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else if (r) k_update<T, L, true, false><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else if (d) k_update<T, L, false, true><<<grid, block, 0, st>>>(g, a, n0, n1);
-    else k_update<T, L, false, false><<<grid, block, 0, st>>>(g, a, n0, n1);
+    if (a.tab) prep_dispatch<true>(g, a, n0, n1, grid, block, st);
+    else prep_dispatch<false>(g, a, n0, n1, grid, block, st);
+    return launched("prep");
 }
 
 int launch_update(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st)
@@ -156,12 +224,110 @@ int launch_update(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t
     if (n1 < n0) return SWCU_OK;
     const dim3 block(BX, BY, 1);
     const dim3 grid((unsigned)((g.nx_end - g.nx_start + BX) / BX), (unsigned)((n1 - n0 + BY) / BY), 1);
-    if (a.trans && a.lat) update_dispatch<true, true>(g, a, n0, n1, grid, block, st);
-    else if (a.trans) update_dispatch<true, false>(g, a, n0, n1, grid, block, st);
-    else if (a.lat) update_dispatch<false, true>(g, a, n0, n1, grid, block, st);
-    else update_dispatch<false, false>(g, a, n0, n1, grid, block, st);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, "update");
+    if (a.tab) update_dispatch<true>(g, a, n0, n1, grid, block, st);
+    else update_dispatch<false>(g, a, n0, n1, grid, block, st);
+    return launched("update");
+}
+
+namespace {
+template <class CFG, bool T, bool L, bool R, bool D>
+int step_launch(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_step<CFG, T, L, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)CFG::SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_step)");
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)((g.nx_end - g.nx_start + TX) / TX), (unsigned)((n1 - n0 + CFG::TY) / CFG::TY), 1);
+    k_step<CFG, T, L, R, D><<<grid, CFG::THREADS, CFG::SMEM, st>>>(maps, g, a, n0, n1);
+    return launched("step_tiled");
+}
+
+template <class CFG>
+int step_dispatch(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st)
+{
+    const bool r = a.RHSx != nullptr, d = a.rdis != nullptr;
+    if (a.trans && a.lat && !r && !d) return step_launch<CFG, true, true, false, false>(maps, g, a, n0, n1, st);
+    if (a.trans && a.lat && !r && d) return step_launch<CFG, true, true, false, true>(maps, g, a, n0, n1, st);
+    if (a.trans && a.lat && r && d) return step_launch<CFG, true, true, true, true>(maps, g, a, n0, n1, st);
+    if (a.trans && a.lat && r && !d) return step_launch<CFG, true, true, true, false>(maps, g, a, n0, n1, st);
+    return -1;  // other flag combinations use the two-launch path
+}
+}  // namespace
+
+// One launch for rows [n0..n1]: needs the per-row metric tables (a.tab) and the eight tensor maps.
+// Returns -1 if this flag combination has no tiled instantiation (caller falls back to two launches).
+int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, int variant, cudaStream_t st)
+{
+    if (n1 < n0) return SWCU_OK;
+    switch (variant) {
+        case 1: return step_dispatch<TileCfg<16, 2, 2>>(maps, g, a, n0, n1, st);
+        case 2: return step_dispatch<TileCfg<16, 1, 2>>(maps, g, a, n0, n1, st);
+        case 3: return step_dispatch<TileCfg<8, 1, 3>>(maps, g, a, n0, n1, st);
+        case 4: return step_dispatch<TileCfg<8, 2, 4>>(maps, g, a, n0, n1, st);
+        case 5: return step_dispatch<TileCfg<16, 4, 2>>(maps, g, a, n0, n1, st);
+        default: return step_dispatch<TileCfg<16, 2, 2>>(maps, g, a, n0, n1, st);
+    }
+}
+
+bool step_tiled_supported(const FusedArgs &a) { return a.trans && a.lat && a.tab != nullptr; }
+
+// TMA box (columns, rows) of a tile variant
+void step_tile_box(int variant, int *box_w, int *box_h)
+{
+    *box_w = IW;
+    *box_h = (variant == 3 || variant == 4 ? 8 : 16) + 2 * HALO;
+}
+
+// ---- per-row metric tables ----------------------------------------------------------------------
+namespace {
+
+// One thread per row: the table entries, evaluated exactly like MetGen does for column nx_start.
+__global__ void k_build_tables(Geo g, MetGen mg, double *__restrict__ tab, int h)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= h) return;
+    const long c = (long)r * g.pitch + (g.nx_start - g.bx1);
+    tab[T_DX * h + r] = mg.dx(c, r);     tab[T_DY * h + r] = mg.dy(c, r);
+    tab[T_DXT * h + r] = mg.dxt(c, r);   tab[T_DYT * h + r] = mg.dyt(c, r);
+    tab[T_DXH * h + r] = mg.dxh(c, r);   tab[T_DYH * h + r] = mg.dyh(c, r);
+    tab[T_DXB * h + r] = mg.dxb(c, r);   tab[T_DYB * h + r] = mg.dyb(c, r);
+    tab[T_RLH * h + r] = mg.rlh(c, r);
+    tab[T_AREA * h + r] = mg.area(c, r);
+    tab[T_DY2 * h + r] = mg.dy2(c, r);   tab[T_DX2 * h + r] = mg.dx2(c, r);
+    tab[T_DXB2 * h + r] = mg.dxb2(c, r); tab[T_DYB2 * h + r] = mg.dyb2(c, r);
+    tab[T_RYX * h + r] = mg.ryx(c, r);   tab[T_RXY * h + r] = mg.rxy(c, r);
+    tab[T_RXYB * h + r] = mg.rxyb(c, r); tab[T_RYXB * h + r] = mg.ryxb(c, r);
+}
+
+// *nonrow += number of cells in columns [bx1+1 .. bx2-1] whose nine real(4) metric values differ
+// (bitwise) from the value in column nx_start of the same row.  The outermost columns are the
+// reference's never-read zero frame and are excluded.
+__global__ void k_check_rowconst(Geo g, const float *const *arrs, int narr, int *nonrow)
+{
+    const int m = g.bx1 + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (m > g.bx2 - 1) return;
+    const long c = (long)r * g.pitch + (m - g.bx1);
+    const long c0 = (long)r * g.pitch + (g.nx_start - g.bx1);
+    int bad = 0;
+    for (int k = 0; k < narr; ++k)
+        bad |= __float_as_int(arrs[k][c]) != __float_as_int(arrs[k][c0]);
+    if (bad) atomicAdd(nonrow, 1);
+}
+
+}  // namespace
+
+int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, int *nonrow_dev,
+                        const float *const *arr_list_dev, cudaStream_t st)
+{
+    const MetGen mg{a.dx, a.dy, a.dxt, a.dyt, a.dxh, a.dyh, a.dxb, a.dyb, a.rlh_s};
+    k_build_tables<<<(unsigned)((h + 127) / 128), 128, 0, st>>>(g, mg, tab, h);
+    const int wcols = g.bx2 - g.bx1 - 1;
+    k_check_rowconst<<<dim3((unsigned)((wcols + 255) / 256), (unsigned)h, 1), 256, 0, st>>>(g, arr_list_dev, 9, nonrow_dev);
+    return launched("build_tables");
 }
 
 // ---- mask packing -----------------------------------------------------------------------------
@@ -184,14 +350,12 @@ __global__ void k_mask_get(long total, float *__restrict__ dst, const unsigned c
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st)
 {
     k_mask_set<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, src, bits, bit);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, "mask_set");
+    return launched("mask_set");
 }
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st)
 {
     k_mask_get<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, dst, bits, bit);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, "mask_get");
+    return launched("mask_get");
 }
 
 }  // namespace swcu

@@ -28,7 +28,8 @@ inline int launched(const char *what)
     if (m > (m1) || n > (n1)) return;                      \
     const long c = ix(g, m, n);                            \
     const int p = g.pitch;                                 \
-    (void)p
+    const int r = n - g.by1;                               \
+    (void)p; (void)r
 
 // K1 -- kernel/shallow_water/vel_ssh.f90:94-104
 __global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, double tau,
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, double tau,
         const double *__restrict__ sshp, const double *__restrict__ u, const double *__restrict__ v)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
-    if (on(lu[c])) sshn[c] = f_sshn(c, p, tau, dx, dy, dxh, dyh, hhu, hhv, sshp, u, v);
+    const MetGen mg{dx, dy, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
+    if (on(lu[c])) sshn[c] = f_sshn(c, r, p, tau, mg, hhu, hhv, sshp, u, v);
 }
 
 // K7 -- kernel/shallow_water/vel_ssh.f90:163-193
@@ -58,12 +60,13 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, double tau,
         const double *__restrict__ RHSx_dif, const double *__restrict__ RHSy_dif)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
+    const MetGen mg{nullptr, nullptr, dxt, dyt, dxh, dyh, dxb, dyb, rlh_s};
     if (on(lcu[c]))
-        un[c] = f_un(c, p, tau, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
-                     rdis[c] + rdis[c + 1], dxt, dyh, dxb, dyb, rlh_s, hhh, ssh, v, up);
+        un[c] = f_un(c, r, p, tau, mg, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
+                     (double)(rdis[c] + rdis[c + 1]), hhh, ssh, v, up);
     if (on(lcv[c]))
-        vn[c] = f_vn(c, p, tau, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
-                     rdis[c] + rdis[c + p], dyt, dxh, dxb, dyb, rlh_s, hhh, ssh, u, vp);
+        vn[c] = f_vn(c, r, p, tau, mg, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
+                     (double)(rdis[c] + rdis[c + p]), hhh, ssh, u, vp);
 }
 
 // K8 -- kernel/shallow_water/vel_ssh.f90:226-243 (range grown by one cell)
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(BX *BY) k_uv_trans_vort(Geo g, const float *__
         const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ vort)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
-    if (on(luu[c])) vort[c] = f_vort(c, p, dxt, dyt, dxb, dyb, u, v);
+    const MetGen mg{nullptr, nullptr, dxt, dyt, nullptr, nullptr, dxb, dyb, nullptr};
+    if (on(luu[c])) vort[c] = f_vort(c, r, p, mg, u, v);
 }
 
 // K4 -- kernel/shallow_water/vel_ssh.f90:318-371
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g,
         double *__restrict__ RHSx, double *__restrict__ RHSy)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
-    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, p, luu[c], luu[c - p], dxh, dyh, u, v, vort, hu, hv, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, p, dxh, dyh, u, v, vort, hu, hv, hh);
+    const MetGen mg{nullptr, nullptr, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
+    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, r, p, mg, (double)luu[c], (double)luu[c - p], u, v, vort, hu, hv, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, r, p, mg, u, v, vort, hu, hv, hh);
 }
 
 // K6 -- kernel/shallow_water/vel_ssh.f90:414-450
@@ -123,8 +128,9 @@ __global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g,
         double *__restrict__ RHSx, double *__restrict__ RHSy)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
-    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, p, hq[c], hq[c + 1], dy, dxt, dyh, dxb, mu, str_t, str_s, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, p, hq[c], hq[c + p], dx, dyt, dxh, dyb, mu, str_t, str_s, hh);
+    const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
+    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, r, p, mg, hq[c], hq[c + 1], mu, str_t, str_s, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, r, p, mg, hq[c], hq[c + p], mu, str_t, str_s, hh);
 }
 
 // K5 -- kernel/shallow_water/mixing.f90:38-56
@@ -138,8 +144,9 @@ __global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g,
         double *__restrict__ str_t, double *__restrict__ str_s)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
-    if (on(lu[c])) str_t[c] = f_str_t(c, p, dx, dy, dxh, dyh, u, v);
-    if (on(luu[c])) str_s[c] = f_str_s(c, p, dxt, dyt, dxb, dyb, u, v);
+    const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
+    if (on(lu[c])) str_t[c] = f_str_t(c, r, p, mg, u, v);
+    if (on(luu[c])) str_s[c] = f_str_s(c, r, p, mg, u, v);
 }
 
 // the three interpolations of hh_init / hh_update for one source depth (depth.f90:57-94);
@@ -155,7 +162,7 @@ __device__ __forceinline__ Interp3 interp3(double q_c, double q_e, double q_n, d
     r.hu = f_interp2(q_c, q_e, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e], dxt, dyh);
     r.hv = f_interp2(q_c, q_n, dx[c], dy[c], lu[c], dx[no], dy[no], lu[no], dxh, dyt);
     r.hh = f_interp4(q_c, q_e, q_n, q_en, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e],
-                     dx[no], dy[no], lu[no], dx[en], dy[en], lu[en], dxb, dyb);
+                     dx[no], dy[no], lu[no], dx[en], dy[en], lu[en], dxb, dyb);  // floats promote exactly
     return r;
 }
 
@@ -181,14 +188,14 @@ __global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, double ffs,
     const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
     if (!(wu || wv || wh)) return;
     const float a = dxt[c], b = dyt[c], cc = dxh[c], d = dyh[c], ee = dxb[c], f = dyb[c];
-    const Interp3 r = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs,
+    const Interp3 i0 = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs,
                               c, p, lu, dx, dy, a, b, cc, d, ee, f);
-    const Interp3 rp = interp3(qp, h_r[e] + shp[e] * ffs, h_r[no] + shp[no] * ffs, h_r[en] + shp[en] * ffs,
+    const Interp3 ip = interp3(qp, h_r[e] + shp[e] * ffs, h_r[no] + shp[no] * ffs, h_r[en] + shp[en] * ffs,
                                c, p, lu, dx, dy, a, b, cc, d, ee, f);
-    const Interp3 rn = interp3(qn, h_r[e], h_r[no], h_r[en], c, p, lu, dx, dy, a, b, cc, d, ee, f);
-    if (wu) { hu[c] = r.hu; hup[c] = rp.hu; hun[c] = rn.hu; }
-    if (wv) { hv[c] = r.hv; hvp[c] = rp.hv; hvn[c] = rn.hv; }
-    if (wh) { hh[c] = r.hh; hhp[c] = rp.hh; hhn[c] = rn.hh; }
+    const Interp3 in = interp3(qn, h_r[e], h_r[no], h_r[en], c, p, lu, dx, dy, a, b, cc, d, ee, f);
+    if (wu) { hu[c] = i0.hu; hup[c] = ip.hu; hun[c] = in.hu; }
+    if (wv) { hv[c] = i0.hv; hvp[c] = ip.hv; hvn[c] = in.hv; }
+    if (wh) { hh[c] = i0.hh; hhp[c] = ip.hh; hhn[c] = in.hh; }
 }
 
 // K2 -- kernel/shallow_water/depth.f90:129-160
@@ -209,11 +216,11 @@ __global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g,
     const long e = c + 1, no = c + p, en = c + 1 + p;
     const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
     if (!(wu || wv || wh)) return;
-    const Interp3 rn = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, p, lu, dx, dy,
+    const Interp3 in = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, p, lu, dx, dy,
                                dxt[c], dyt[c], dxh[c], dyh[c], dxb[c], dyb[c]);
-    if (wu) hun[c] = rn.hu;
-    if (wv) hvn[c] = rn.hv;
-    if (wh) hhn[c] = rn.hh;
+    if (wu) hun[c] = in.hu;
+    if (wv) hvn[c] = in.hv;
+    if (wh) hhn[c] = in.hh;
 }
 
 // K9 -- kernel/shallow_water/depth.f90:185-209

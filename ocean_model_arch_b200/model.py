@@ -233,6 +233,13 @@ class DeviceBlock:
     def step(self, tau, nsteps=1):
         check(self.L.swcu_step(self.h, float(tau), int(nsteps)))
 
+    def set_option(self, name, value):
+        check(self.L.swcu_set_option(self.h, name.encode(), int(value)))
+
+    @property
+    def uses_metric_tables(self):
+        return bool(self.L.swcu_uses_metric_tables(self.h))
+
     def synchronize(self):
         bad = C.c_long()
         check(self.L.swcu_synchronize(self.h, C.byref(bad)))

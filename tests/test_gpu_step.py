@@ -65,9 +65,7 @@ def test_against_live_oracle_all_state_fields(swlib, cuda_device, mode):
                   "hhv_n", "hhh", "hhh_p", "hhh_n", "vort", "str_t", "str_s", "RHSx_adv", "RHSy_adv",
                   "RHSx_dif", "RHSy_dif"):
             assert np.array_equal(m.get(f), o.get(f)), f
-    else:                          # scratch of the fused path holds the reference's last-step values
-        for f in ("vort", "str_t", "str_s"):
-            assert np.array_equal(m.get(f), o.get(f)), f
+
 
 
 @pytest.mark.parametrize("flags", [dict(full_free_surface=0), dict(trans_terms=0, ksw_lat=0), dict(ksw_lat=0)])
@@ -111,7 +109,7 @@ def test_fused_equals_reference_sequence_at_2048(swlib, cuda_device):
         x, y = a.get(f), b.get(f)
         assert np.array_equal(x, y), f
         assert np.isfinite(x).all()
-    assert b.block.launches == 40 and a.block.launches == 20 * 11 + 1
+    assert b.block.launches == 20 and a.block.launches == 20 * 11 + 1   # one TMA-tiled launch per step
 
 
 def test_blowup_flag(swlib, cuda_device):
@@ -125,3 +123,62 @@ def test_blowup_flag(swlib, cuda_device):
     with pytest.raises(SwcuError) as e:
         m.block.synchronize()
     assert e.value.code == 5
+
+
+def test_metric_tables_and_general_path_agree(swlib, cuda_device):
+    """The per-row metric tables (MetRow) and the 2-D real(4) arrays (MetGen) give the same bits;
+    a grid whose metrics vary along m must fall back to MetGen automatically and still match the
+    oracle given the same arrays."""
+    nx, ny = 90, 61
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    a = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    b = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    b.block.set_option("metric_tables", 0)
+    t = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    t.block.set_option("tiled", 0)          # tables, but two launches from global memory
+    o.step(30); a.step(30); b.step(30); t.step(30)
+    assert a.block.uses_metric_tables and t.block.uses_metric_tables and not b.block.uses_metric_tables
+    assert (a.block.launches, t.block.launches, b.block.launches) == (30, 60, 60)
+    for f in STATE:
+        assert np.array_equal(a.get(f), o.get(f)), f
+        assert np.array_equal(b.get(f), o.get(f)), f
+        assert np.array_equal(t.get(f), o.get(f)), f
+    # m-dependent Coriolis and dx (as a rotated / curvilinear grid would give)
+    rng = np.random.default_rng(3)
+    o2 = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    c = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    for f in ("rlh_s", "dx", "dyh"):
+        arr = (o2.get(f) * (1.0 + 0.01 * rng.random((ny, nx)))).astype(np.float32)
+        o2.set(f, arr)
+        c.block.upload(f, arr)
+    # the oracle's depth fields were initialised with the old dx: redo hh_init through a step-0 trick
+    o3 = OracleModel(make_config(nx, ny, keep_mu=1, full_free_surface=0), mask)   # (unused, keeps API symmetric)
+    del o3
+    # re-derive the oracle's depth arrays from its (modified) metrics exactly like init does
+    from oracle_lib import call_kernel
+    d = o2.block_dims(0)
+    f4 = {n: o2.get(n) for n in ("lu", "llu", "llv", "luh", "dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb")}
+    outs = {n: o2.get(n) for n in ("hhq", "hhq_p", "hhq_n", "hhu", "hhu_p", "hhu_n", "hhv", "hhv_p", "hhv_n",
+                                   "hhh", "hhh_p", "hhh_n")}
+    call_kernel("hh_init_kernel", d, 1, *[f4[n] for n in f4], *[outs[n] for n in outs],
+                o2.get("ssh"), o2.get("sshp"), o2.get("hhq_rest"))
+    for n, arr in outs.items():
+        o2.set(n, arr)
+    o2.step(20); c.step(20)
+    assert not c.block.uses_metric_tables
+    for f in STATE:
+        assert np.array_equal(c.get(f), o2.get(f)), f
+
+
+@pytest.mark.parametrize("shape", [(36, 23), (37, 40), (68, 21), (101, 53)])
+def test_ragged_tiles(swlib, cuda_device, shape):
+    """Basin sizes that leave partial 32x16 tiles on the right / top edge of the tiled kernel."""
+    nx, ny = shape
+    mask = basins.island_mask(nx, ny, ndisc=2)
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    o.step(15); m.step(15)
+    assert m.block.uses_metric_tables
+    for f in STATE:
+        assert np.array_equal(m.get(f), o.get(f)), (f, shape)
