@@ -253,6 +253,12 @@ void *swcu_stream(swcu_ctx *ctx);
 int swcu_comm_unique_id(void *id128);
 int swcu_comm_init(swcu_ctx *ctx, int nranks, int rank, const void *id128);
 int swcu_comm_destroy(swcu_ctx *ctx);
+/* The row bookkeeping of the halo exchange, exposed so hosts can test it without a GPU: for the
+ * neighbour below (side = 0, rank-1) or above (side = 1, rank+1) and a halo of `nrows` rows, the
+ * 0-based array row where the rows to SEND start and where the RECEIVED rows land
+ * (array row of reference row n is n - bnd_y1; get_boundary_points_of_block /
+ * get_halo_points_of_block, core/decomposition.f90:94-154, 230-290, widened to nrows). */
+int swcu_halo_plan(const swcu_dims *dims, int nrows, int side, int *send_row, int *recv_row);
 /* One explicit halo exchange of a field (all ranks call it): the analogue of
  * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use. */
 int swcu_halo_exchange(swcu_ctx *ctx, int field);

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "swcu_comm_unique_id": [_P],
     "swcu_comm_init": [_P, _I, _I, _P],
     "swcu_comm_destroy": [_P],
+    "swcu_halo_plan": [_DIMS, _I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swcu_halo_exchange": [_P, _I],
     "swcu_last_error": [],
     "swcu_version": [],

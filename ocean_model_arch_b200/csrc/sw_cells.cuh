@@ -27,15 +27,15 @@ __device__ __forceinline__ PrepOut prep_cell(long c, int r, int p, const M &mt, 
     const unsigned char mb = mask[c];
     const double q_c = h_r[c] + ssh[c] * ffs, q_e = h_r[e] + ssh[e] * ffs;
     const double q_n = h_r[no] + ssh[no] * ffs, q_en = h_r[en] + ssh[en] * ffs;
-    const double lu_c = md(mb, MB_LU), lu_e = md(mask[e], MB_LU);
-    const double lu_n = md(mask[no], MB_LU), lu_en = md(mask[en], MB_LU);
+    const int b_c = mb & MB_LU, b_e = mask[e] & MB_LU, b_n = mask[no] & MB_LU, b_en = mask[en] & MB_LU;  // 0 / 1
+    const double lu_c = b_c ? 1.0 : 0.0, lu_e = b_e ? 1.0 : 0.0, lu_n = b_n ? 1.0 : 0.0, lu_en = b_en ? 1.0 : 0.0;
     const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r), dx_e = mt.dx(e, r), dy_e = mt.dy(e, r);
     const double dx_n = mt.dx(no, r + 1), dy_n = mt.dy(no, r + 1), dx_en = mt.dx(en, r + 1), dy_en = mt.dy(en, r + 1);
     PrepOut o;
-    const double hu = f_interp2(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, mt.dxt(c, r), mt.dyh(c, r));
-    const double hv = f_interp2(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, mt.dxh(c, r), mt.dyt(c, r));
-    const double hh = f_interp4(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
-                                dx_en, dy_en, lu_en, mt.dxb(c, r), mt.dyb(c, r));
+    const double hu = f_interp2_b(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, b_c + b_e, mt.dxt(c, r), mt.dyh(c, r));
+    const double hv = f_interp2_b(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, b_c + b_n, mt.dxh(c, r), mt.dyt(c, r));
+    const double hh = f_interp4_b(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
+                                  dx_en, dy_en, lu_en, b_c + b_e + b_n + b_en, mt.dxb(c, r), mt.dyb(c, r));
     o.hu = (mb & MB_LLU) ? hu : 0.0;
     o.hv = (mb & MB_LLV) ? hv : 0.0;
     o.hh = (mb & MB_LUH) ? hh : 0.0;
@@ -58,7 +58,7 @@ struct UpdOut { double ssh, sshp, u, up, v, vp; int bad; };
 // masks select at the end (branch-free; masked lanes may carry Inf/NaN that are never stored).
 // rhsx / rhsy / rdx / rdy: RHSx(m,n), RHSy(m,n), dble(rdis(m,n)+rdis(m+1,n)), dble(rdis(m,n)+rdis(m,n+1)).
 template <bool TRANS, bool LAT, class M>
-__device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt, double tau, double ts, double ffs,
+__device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt, const Tau &tau, double ts, double ffs,
         const unsigned char *__restrict__ mask,
         const double *__restrict__ ssh, const double *__restrict__ sshp,
         const double *__restrict__ u, const double *__restrict__ up,
@@ -75,7 +75,7 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
     UpdOut o;
 
     // K1 + K8 + K11
-    const double sshn = f_sshn(c, r, p, tau, mt, hu, hv, sshp, u, v);
+    const double sshn = f_sshn(c, r, p, tau.tau, mt, hu, hv, sshp, u, v);
     const bool sea = mb & MB_LU;
     o.ssh = sea ? sshn : ssh_c;
     o.sshp = sea ? f_filter(ssh_c, sshn, sshp_c, ts) : sshp_c;  // vel_ssh.f90:230-231
@@ -84,13 +84,15 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
     const double h_c = h_r[c];
     const double q_c = h_c + ssh_c * ffs, qp_c = h_c + sshp_c * ffs;
     const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r);
-    const double lu_c = md(mb, MB_LU);
+    const int b_c = mb & MB_LU;
+    const double lu_c = b_c ? 1.0 : 0.0;
     {   // zonal velocity: K10 (shp), K4, K6, K7, K8
         const double h_e = h_r[e];
         const double q_e = h_e + ssh[e] * ffs, qp_e = h_e + sshp[e] * ffs;
         const double hu_c = hu[c];
-        const double hup_c = f_interp2(qp_c, qp_e, dx_c, dy_c, lu_c, mt.dx(e, r), mt.dy(e, r), md(mask[e], MB_LU),
-                                       mt.dxt(c, r), mt.dyh(c, r));  // depth.f90:62-63
+        const int b_e = mask[e] & MB_LU;
+        const double hup_c = f_interp2_b(qp_c, qp_e, dx_c, dy_c, lu_c, mt.dx(e, r), mt.dy(e, r), b_e ? 1.0 : 0.0,
+                                         b_c + b_e, mt.dxt(c, r), mt.dyh(c, r));  // depth.f90:62-63
         const double adv = TRANS ? f_rhsx_adv(c, r, p, mt, md(mb, MB_LUU), md(mask[c - p], MB_LUU),
                                               u, v, vort, hu, hv, hh) : 0.0;
         const double dif = LAT ? f_rhsx_dif(c, r, p, mt, q_c, q_e, mu, str_t, str_s, hh) : 0.0;
@@ -103,8 +105,9 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
         const double h_n = h_r[no];
         const double q_n = h_n + ssh[no] * ffs, qp_n = h_n + sshp[no] * ffs;
         const double hv_c = hv[c];
-        const double hvp_c = f_interp2(qp_c, qp_n, dx_c, dy_c, lu_c, mt.dx(no, r + 1), mt.dy(no, r + 1),
-                                       md(mask[no], MB_LU), mt.dxh(c, r), mt.dyt(c, r));  // depth.f90:73-74
+        const int b_n = mask[no] & MB_LU;
+        const double hvp_c = f_interp2_b(qp_c, qp_n, dx_c, dy_c, lu_c, mt.dx(no, r + 1), mt.dy(no, r + 1),
+                                         b_n ? 1.0 : 0.0, b_c + b_n, mt.dxh(c, r), mt.dyt(c, r));  // depth.f90:73-74
         const double adv = TRANS ? f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh) : 0.0;
         const double dif = LAT ? f_rhsy_dif(c, r, p, mt, q_c, q_n, mu, str_t, str_s, hh) : 0.0;
         const double vn = f_vn(c, r, p, tau, mt, hv_c, hv_c, hvp_c, rhsy, dif, adv, rdy, hh, ssh, u, vp);

@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -93,6 +94,8 @@ int encode_load()
     return SWCU_OK;
 }
 
+#define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
+
 const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
 
 int mask_bit(int field)
@@ -139,7 +142,7 @@ struct swcu_ctx {
     const float **arr_list_dev = nullptr;
     int *nonrow_dev = nullptr;
     bool want_tiled = true;                   // one-launch TMA-tiled step when the tables are usable
-    int tile_variant = 1;
+    int tile_variant = 3;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
     // per-launch event pairs, filled only inside swcu_profile_steps
     bool prof = false;
@@ -207,16 +210,13 @@ int exchange_rows(swcu_ctx *c, T *base, int nrows, cudaStream_t st)
 {
     const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
     const size_t cnt = (size_t)nrows * c->pitch;
-    const int lo = c->rank - 1, hi = c->rank + 1;
-    // row index (0-based in the array) of reference row n is n - bnd_y1
-    const long r_first = c->d.ny_start - c->d.bnd_y1, r_last = c->d.ny_end - c->d.bnd_y1;
-    if (lo >= 0) {
-        SWCU_NCCL(g_nccl.Send(base + (size_t)r_first * c->pitch, cnt, dt, lo, c->comm, st));
-        SWCU_NCCL(g_nccl.Recv(base + (size_t)(r_first - nrows) * c->pitch, cnt, dt, lo, c->comm, st));
-    }
-    if (hi < c->nranks) {
-        SWCU_NCCL(g_nccl.Send(base + (size_t)(r_last - nrows + 1) * c->pitch, cnt, dt, hi, c->comm, st));
-        SWCU_NCCL(g_nccl.Recv(base + (size_t)(r_last + 1) * c->pitch, cnt, dt, hi, c->comm, st));
+    const int peer[2] = {c->rank - 1, c->rank + 1};
+    for (int side = 0; side < 2; ++side) {
+        if (peer[side] < 0 || peer[side] >= c->nranks) continue;
+        int srow = 0, rrow = 0;
+        RC(swcu_halo_plan(&c->d, nrows, side, &srow, &rrow));
+        SWCU_NCCL(g_nccl.Send(base + (size_t)srow * c->pitch, cnt, dt, peer[side], c->comm, st));
+        SWCU_NCCL(g_nccl.Recv(base + (size_t)rrow * c->pitch, cnt, dt, peer[side], c->comm, st));
     }
     return SWCU_OK;
 }
@@ -231,8 +231,6 @@ int sync_fields(swcu_ctx *c, std::initializer_list<int> fields)
     SWCU_NCCL(g_nccl.GroupEnd());
     return SWCU_OK;
 }
-
-#define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
 int prof_mark(swcu_ctx *c, int kind, bool begin)
 {
@@ -400,7 +398,12 @@ int step_fused(swcu_ctx *c, double tau)
     a.vort = c->f8[SWCU_F_VORT]; a.str_t = c->f8[SWCU_F_STR_T]; a.str_s = c->f8[SWCU_F_STR_S];
     fill_static_args(c, a);
     a.tab = c->use_tables ? c->tab : nullptr; a.tab_h = c->h;
-    a.tau = tau; a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
+    {   // x/tau == x*(1/tau) bitwise when tau is a power of two (exact scaling)
+        int ex = 0;
+        const double mant = frexp(tau, &ex);
+        a.tau.tau = tau; a.tau.rtau = 1.0 / tau; a.tau.pow2 = (mant == 0.5 && tau > 1e-300 && tau < 1e300) ? 1 : 0;
+    }
+    a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
     a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;
 
     const int ns = g.ny_start, ne = g.ny_end;
@@ -568,7 +571,12 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
 #define TRY(call) do { if (!rc) rc = (call); } while (0)
 #define TRYCUDA(call) do { if (!rc) { cudaError_t e__ = (call); if (e__ != cudaSuccess) rc = cuda_fail(e__, #call); } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    TRYCUDA(cudaStreamCreateWithFlags(&c->comm_st, cudaStreamNonBlocking));
+    {   // the halo-exchange stream outranks the compute stream so NCCL's copy kernel is scheduled as
+        // soon as an SM frees up instead of queueing behind the interior update's CTAs
+        int lo = 0, hi = 0;
+        TRYCUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TRYCUDA(cudaStreamCreateWithPriority(&c->comm_st, cudaStreamNonBlocking, hi));
+    }
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreate(&c->t0));
@@ -754,6 +762,19 @@ int swcu_comm_destroy(swcu_ctx *c)
     cudaDeviceSynchronize();
     SWCU_NCCL(g_nccl.CommDestroy(c->comm));
     c->comm = nullptr; c->nranks = 1; c->rank = 0;
+    return SWCU_OK;
+}
+
+int swcu_halo_plan(const swcu_dims *d, int nrows, int side, int *send_row, int *recv_row)
+{
+    if (!d || !send_row || !recv_row || nrows < 1 || nrows > 2 || (side != 0 && side != 1)) {
+        set_error("bad halo plan arguments");
+        return SWCU_ERR_ARG;
+    }
+    const int r_first = d->ny_start - d->bnd_y1, r_last = d->ny_end - d->bnd_y1;
+    if (r_last - r_first + 1 < nrows) { set_error("block has fewer interior rows than the halo width"); return SWCU_ERR_ARG; }
+    if (side == 0) { *send_row = r_first; *recv_row = r_first - nrows; }
+    else { *send_row = r_last - nrows + 1; *recv_row = r_last + 1; }
     return SWCU_OK;
 }
 

@@ -68,10 +68,11 @@ enum MetTab : int {
 };
 
 struct MetRow {
-    const double *tab;  // [T_COUNT][h]
+    const double *tab;  // [T_COUNT][h]: global tables, or a shared-memory copy of rows r0 .. r0+h-1
     int h;
+    int r0;
 #define SWCU_ROW(name, T) \
-    __device__ __forceinline__ double name(long, int r) const { return __ldg(tab + (T) * h + r); }
+    __device__ __forceinline__ double name(long, int r) const { return tab[(T) * h + (r - r0)]; }
     SWCU_ROW(dx, T_DX) SWCU_ROW(dy, T_DY) SWCU_ROW(dxt, T_DXT) SWCU_ROW(dyt, T_DYT)
     SWCU_ROW(dxh, T_DXH) SWCU_ROW(dyh, T_DYH) SWCU_ROW(dxb, T_DXB) SWCU_ROW(dyb, T_DYB)
     SWCU_ROW(rlh, T_RLH) SWCU_ROW(area, T_AREA) SWCU_ROW(dy2, T_DY2) SWCU_ROW(dx2, T_DX2)
@@ -101,6 +102,29 @@ __device__ __forceinline__ double f_interp2(double hq_c, double hq_e,
 {
     const double slu = lu_c + lu_e;
     return (hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e) / slu / d1 / d2;
+}
+
+// x / slu for slu = dble(lu+lu[+lu+lu]) with 0/1 masks, nsea = number of sea cells among them.
+// Division by 1, 2, 4 is an exact scaling, so multiplying by the exact reciprocal gives the same
+// bits as the reference's division; 3 keeps the true division.  (nsea = 0 only on masked-out cells.)
+__device__ __forceinline__ double div_slu(double x, int nsea)
+{
+    if (nsea == 3) return x / 3.0;
+    return x * (nsea == 2 ? 0.5 : (nsea == 4 ? 0.25 : 1.0));
+}
+
+// f_interp2 / f_interp4 for masks known to be exactly 0 or 1 (fused path: masks come from bits)
+__device__ __forceinline__ double f_interp2_b(double hq_c, double hq_e,
+        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e, int nsea, double d1, double d2)
+{
+    return div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e, nsea) / d1 / d2;
+}
+__device__ __forceinline__ double f_interp4_b(double hq_c, double hq_e, double hq_n, double hq_en,
+        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e,
+        double dx_n, double dy_n, double lu_n, double dx_en, double dy_en, double lu_en, int nsea, double dxb, double dyb)
+{
+    return div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e
+                 + hq_n * dx_n * dy_n * lu_n + hq_en * dx_en * dy_en * lu_en, nsea) / dxb / dyb;
 }
 
 // kernel/shallow_water/depth.f90:81-85
@@ -200,10 +224,18 @@ __device__ __forceinline__ double f_rhsy_dif(long c, int r, int p, const M &m, d
          + (m.dyb2(c, r) * muh_p * hh[c] * str_s[c] - m.dyb2(w, r) * muh_m * hh[w] * str_s[w]) / m.dyt(c, r);
 }
 
+// x / tau.  When tau is a power of two the division is an exact scaling and x * (1/tau) gives the
+// same bits (the host checks frexp(tau) == 0.5 * 2^e); otherwise the true division is kept.
+struct Tau {
+    double tau, rtau;
+    int pow2;
+    __device__ __forceinline__ double div(double x) const { return pow2 ? x * rtau : x / tau; }
+};
+
 // kernel/shallow_water/vel_ssh.f90:167-176 ; FreeFallAcc is real(4) 9.8 promoted;
 // rd = dble(rdis(m,n)+rdis(m+1,n)), the real(4) sum promoted
 template <class M>
-__device__ __forceinline__ double f_un(long c, int r, int p, double tau, const M &m,
+__device__ __forceinline__ double f_un(long c, int r, int p, const Tau &tau, const M &m,
         double hu_c, double hun_c, double hup_c, double rhsx, double rhsx_dif, double rhsx_adv, double rd,
         const double *__restrict__ hhh, const double *__restrict__ ssh,
         const double *__restrict__ v, const double *__restrict__ up)
@@ -211,8 +243,8 @@ __device__ __forceinline__ double f_un(long c, int r, int p, double tau, const M
     const long e = c + 1, s = c - p, es = c + 1 - p;
     const double g = (double)9.8f;
     const double dxt = m.dxt(c, r), dyh = m.dyh(c, r);
-    const double bp = hun_c * dxt * dyh / 2.0 / tau;
-    const double bp0 = hup_c * dxt * dyh / 2.0 / tau;
+    const double bp = tau.div(hun_c * dxt * dyh / 2.0);
+    const double bp0 = tau.div(hup_c * dxt * dyh / 2.0);
     const double slx = -g * (ssh[e] - ssh[c]) * dyh * hu_c;
     const double grx = rhsx + slx + rhsx_dif + rhsx_adv
                      - rd / 2.0 * up[c] * dxt * dyh * hu_c
@@ -223,7 +255,7 @@ __device__ __forceinline__ double f_un(long c, int r, int p, double tau, const M
 
 // kernel/shallow_water/vel_ssh.f90:181-190 ; rd = dble(rdis(m,n)+rdis(m,n+1))
 template <class M>
-__device__ __forceinline__ double f_vn(long c, int r, int p, double tau, const M &m,
+__device__ __forceinline__ double f_vn(long c, int r, int p, const Tau &tau, const M &m,
         double hv_c, double hvn_c, double hvp_c, double rhsy, double rhsy_dif, double rhsy_adv, double rd,
         const double *__restrict__ hhh, const double *__restrict__ ssh,
         const double *__restrict__ u, const double *__restrict__ vp)
@@ -231,8 +263,8 @@ __device__ __forceinline__ double f_vn(long c, int r, int p, double tau, const M
     const long w = c - 1, no = c + p, wn = c - 1 + p;
     const double g = (double)9.8f;
     const double dyt = m.dyt(c, r), dxh = m.dxh(c, r);
-    const double bp = hvn_c * dyt * dxh / 2.0 / tau;
-    const double bp0 = hvp_c * dyt * dxh / 2.0 / tau;
+    const double bp = tau.div(hvn_c * dyt * dxh / 2.0);
+    const double bp0 = tau.div(hvp_c * dyt * dxh / 2.0);
     const double sly = -g * (ssh[no] - ssh[c]) * dxh * hv_c;
     const double gry = rhsy + sly + rhsy_dif + rhsy_adv
                      - rd / 2.0 * vp[c] * dxh * dyt * hv_c

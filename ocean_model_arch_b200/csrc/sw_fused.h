@@ -26,7 +26,8 @@ struct FusedArgs {
     int tab_h;
     const unsigned char *mask;
     int *bad;  // K11 counter
-    double tau, ts, ffs;
+    Tau tau;
+    double ts, ffs;
     int trans, lat;
 };
 

@@ -30,7 +30,7 @@ constexpr int BY = 4;
 template <bool ROW> struct MetOf;
 template <> struct MetOf<true> {
     typedef MetRow type;
-    static __device__ __forceinline__ MetRow make(const FusedArgs &a) { return MetRow{a.tab, a.tab_h}; }
+    static __device__ __forceinline__ MetRow make(const FusedArgs &a) { return MetRow{a.tab, a.tab_h, 0}; }
 };
 template <> struct MetOf<false> {
     typedef MetGen type;
@@ -89,7 +89,9 @@ template <int TY_, int R_, int MINB_> struct TileCfg {
     static constexpr int IH = TY + 2 * HALO, TILE = IW * IH;
     static constexpr int THREADS = TX * TY / R;
     static constexpr int MASK_BYTES = (TILE + 127) / 128 * 128;
-    static constexpr size_t SMEM = (size_t)(N_IN + N_S1) * TILE * sizeof(double) + MASK_BYTES + 16;
+    static constexpr int TROWS = IH + 1;  // metric-table rows a tile touches (r .. r+1)
+    static constexpr size_t SMEM = (size_t)(N_IN + N_S1) * TILE * sizeof(double) + MASK_BYTES + 16
+                                 + (size_t)T_COUNT * TROWS * sizeof(double);
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -104,6 +106,7 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
     double *s1 = in + N_IN * TILE;
     unsigned char *mk = reinterpret_cast<unsigned char *>(s1 + N_S1 * TILE);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(mk + CFG::MASK_BYTES);
+    double *stab = reinterpret_cast<double *>(mk + CFG::MASK_BYTES + 16);  // [T_COUNT][TROWS]
 
     const int tid = threadIdx.x;
     const int i0 = g.nx_start + blockIdx.x * TX, j0 = n0 + blockIdx.y * TY;
@@ -129,6 +132,10 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
         const int lx = idx % IW, ly = idx / IW, gx = ax + lx, gy = ay + ly;
         mk[idx] = (gx < w && gy < h) ? a.mask[(long)gy * g.pitch + gx] : (unsigned char)0;
     }
+    for (int idx = tid; idx < T_COUNT * CFG::TROWS; idx += THREADS) {  // this tile's rows of the metric tables
+        const int t = idx / CFG::TROWS, rr = idx % CFG::TROWS;
+        stab[idx] = __ldg(a.tab + (long)t * a.tab_h + ay + rr);   // the table carries slack rows past h
+    }
     {
         unsigned done = 0;
         while (!done)
@@ -141,7 +148,7 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
                  *vp = in + 5 * TILE, *h_r = in + 6 * TILE, *mu = in + 7 * TILE;
     double *hu = s1, *hv = s1 + TILE, *hh = s1 + 2 * TILE, *vort = s1 + 3 * TILE, *str_t = s1 + 4 * TILE,
            *str_s = s1 + 5 * TILE;
-    const MetRow mt{a.tab, a.tab_h};
+    const MetRow mt{stab, CFG::TROWS, ay};
 
     // stage A on the tile grown by one cell: local columns 1..TX+2, rows 1..TY+2
     constexpr int AW = TX + 2, AH = TY + 2;
@@ -268,7 +275,7 @@ int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, in
         case 3: return step_dispatch<TileCfg<8, 1, 3>>(maps, g, a, n0, n1, st);
         case 4: return step_dispatch<TileCfg<8, 2, 4>>(maps, g, a, n0, n1, st);
         case 5: return step_dispatch<TileCfg<16, 4, 2>>(maps, g, a, n0, n1, st);
-        default: return step_dispatch<TileCfg<16, 2, 2>>(maps, g, a, n0, n1, st);
+        default: return step_dispatch<TileCfg<8, 1, 3>>(maps, g, a, n0, n1, st);
     }
 }
 

@@ -1,0 +1,85 @@
+"""Multi-GPU decomposition-invariance check, run under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/run_multi_gpu.py [nx ny steps]
+
+Every rank owns one y-slab of the global basin and exchanges halo rows over NCCL each step.
+Rank 0 also runs the same basin as ONE block on its GPU and (for small basins) on the CPU oracle;
+ssh/sshp/u/up/v/vp of the N-slab run must equal both BITWISE."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STATE = ("ssh", "sshp", "ubrtr", "ubrtrp", "vbrtr", "vbrtrp")
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import basins
+    from ocean_model_arch_b200 import model
+    from ocean_model_arch_b200._lib import MODE_FUSED, MODE_REFERENCE
+
+    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+    ny = int(sys.argv[2]) if len(sys.argv) > 2 else 203
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mask = basins.island_mask(nx, ny)
+    bp = model.BasinPar(nx=nx, ny=ny)
+    ok = True
+    for mode, tiled in ((MODE_FUSED, 1), (MODE_FUSED, 0), (MODE_REFERENCE, 0)):
+        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True)
+        if mode == MODE_FUSED:
+            m.block.set_option("tiled", tiled)
+        ids = [model.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        m.attach_comm(ids[0])
+        m.step(steps)
+        assert m.block.synchronize() == 0
+        d = m.dims
+        rows = slice(d.ny_start - d.bnd_y1, d.ny_end - d.bnd_y1 + 1)
+        parts = {}
+        for f in STATE:
+            mine = torch.from_numpy(m.get(f)[rows].copy()).cuda()
+            sizes = [None] * world
+            dist.all_gather_object(sizes, mine.shape[0])
+            bufs = [torch.empty((s, mine.shape[1]), dtype=mine.dtype, device="cuda") for s in sizes]
+            dist.all_gather(bufs, mine)
+            parts[f] = torch.cat(bufs, 0).cpu().numpy()
+        if rank == 0:
+            one = model.ShallowWaterModel(bp, mask=mask, device=local, mode=MODE_FUSED, keep_mu=True)
+            one.step(steps)
+            for f in STATE:
+                ref = one.get(f)[2:-2]
+                same = np.array_equal(parts[f], ref)
+                ok &= same
+                if not same:
+                    print(f"MISMATCH vs 1-GPU mode={mode} tiled={tiled} {f}: max|d|={np.abs(parts[f] - ref).max()}")
+            if nx * ny <= 400 * 400:
+                from oracle_lib import OracleModel, make_config
+                o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+                o.step(steps)
+                for f in STATE:
+                    same = np.array_equal(parts[f], o.get(f)[2:-2])
+                    ok &= same
+                    if not same:
+                        print(f"MISMATCH vs oracle mode={mode} tiled={tiled} {f}")
+            print(f"mode={mode} tiled={tiled} world={world}: {'bitwise equal' if ok else 'FAILED'} "
+                  f"(launches {m.block.launches})", flush=True)
+        m.block.close()
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,3 +182,19 @@ def test_ragged_tiles(swlib, cuda_device, shape):
     assert m.block.uses_metric_tables
     for f in STATE:
         assert np.array_equal(m.get(f), o.get(f)), (f, shape)
+
+
+@pytest.mark.parametrize("dt", [0.75, 2.0, 0.3])
+def test_time_steps_pow2_and_not(swlib, cuda_device, dt):
+    """tau = 2.0 takes the exact-scaling shortcut for x/tau, 0.75 and 0.3 keep the true division;
+    all must match the oracle bitwise (time_step is real(4) in the reference)."""
+    nx, ny = 70, 50
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, time_step=dt), mask)
+    o.step(25)
+    for mode in (MODE_REFERENCE, MODE_FUSED):
+        m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), model.SwPar(), model.RunPar(time_step=dt), mask=mask,
+                                    mode=mode, keep_mu=True)
+        m.step(25)
+        for f in STATE:
+            assert np.array_equal(m.get(f), o.get(f)), (f, dt, mode)
