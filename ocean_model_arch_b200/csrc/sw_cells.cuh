@@ -32,10 +32,13 @@ __device__ __forceinline__ PrepOut prep_cell(long c, int r, int p, const M &mt, 
     const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r), dx_e = mt.dx(e, r), dy_e = mt.dy(e, r);
     const double dx_n = mt.dx(no, r + 1), dy_n = mt.dy(no, r + 1), dx_en = mt.dx(en, r + 1), dy_en = mt.dy(en, r + 1);
     PrepOut o;
-    const double hu = f_interp2_b(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, b_c + b_e, mt.dxt(c, r), mt.dyh(c, r));
-    const double hv = f_interp2_b(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, b_c + b_n, mt.dxh(c, r), mt.dyt(c, r));
-    const double hh = f_interp4_b(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
-                                  dx_en, dy_en, lu_en, b_c + b_e + b_n + b_en, mt.dxb(c, r), mt.dyb(c, r));
+    const double hu = f_interp2_b<M>(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, b_c + b_e,
+                                     mt.dxt(c, r), mt.r_dxt(c, r), mt.dyh(c, r), mt.r_dyh(c, r));
+    const double hv = f_interp2_b<M>(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n, b_c + b_n,
+                                     mt.dxh(c, r), mt.r_dxh(c, r), mt.dyt(c, r), mt.r_dyt(c, r));
+    const double hh = f_interp4_b<M>(q_c, q_e, q_n, q_en, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e, dx_n, dy_n, lu_n,
+                                     dx_en, dy_en, lu_en, b_c + b_e + b_n + b_en,
+                                     mt.dxb(c, r), mt.r_dxb(c, r), mt.dyb(c, r), mt.r_dyb(c, r));
     o.hu = (mb & MB_LLU) ? hu : 0.0;
     o.hv = (mb & MB_LLV) ? hv : 0.0;
     o.hh = (mb & MB_LUH) ? hh : 0.0;
@@ -91,8 +94,8 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
         const double q_e = h_e + ssh[e] * ffs, qp_e = h_e + sshp[e] * ffs;
         const double hu_c = hu[c];
         const int b_e = mask[e] & MB_LU;
-        const double hup_c = f_interp2_b(qp_c, qp_e, dx_c, dy_c, lu_c, mt.dx(e, r), mt.dy(e, r), b_e ? 1.0 : 0.0,
-                                         b_c + b_e, mt.dxt(c, r), mt.dyh(c, r));  // depth.f90:62-63
+        const double hup_c = f_interp2_b<M>(qp_c, qp_e, dx_c, dy_c, lu_c, mt.dx(e, r), mt.dy(e, r), b_e ? 1.0 : 0.0,
+                                            b_c + b_e, mt.dxt(c, r), mt.r_dxt(c, r), mt.dyh(c, r), mt.r_dyh(c, r));  // depth.f90:62-63
         const double adv = TRANS ? f_rhsx_adv(c, r, p, mt, md(mb, MB_LUU), md(mask[c - p], MB_LUU),
                                               u, v, vort, hu, hv, hh) : 0.0;
         const double dif = LAT ? f_rhsx_dif(c, r, p, mt, q_c, q_e, mu, str_t, str_s, hh) : 0.0;
@@ -106,8 +109,9 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
         const double q_n = h_n + ssh[no] * ffs, qp_n = h_n + sshp[no] * ffs;
         const double hv_c = hv[c];
         const int b_n = mask[no] & MB_LU;
-        const double hvp_c = f_interp2_b(qp_c, qp_n, dx_c, dy_c, lu_c, mt.dx(no, r + 1), mt.dy(no, r + 1),
-                                         b_n ? 1.0 : 0.0, b_c + b_n, mt.dxh(c, r), mt.dyt(c, r));  // depth.f90:73-74
+        const double hvp_c = f_interp2_b<M>(qp_c, qp_n, dx_c, dy_c, lu_c, mt.dx(no, r + 1), mt.dy(no, r + 1),
+                                            b_n ? 1.0 : 0.0, b_c + b_n, mt.dxh(c, r), mt.r_dxh(c, r),
+                                            mt.dyt(c, r), mt.r_dyt(c, r));  // depth.f90:73-74
         const double adv = TRANS ? f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh) : 0.0;
         const double dif = LAT ? f_rhsy_dif(c, r, p, mt, q_c, q_n, mu, str_t, str_s, hh) : 0.0;
         const double vn = f_vn(c, r, p, tau, mt, hv_c, hv_c, hvp_c, rhsy, dif, adv, rdy, hh, ssh, u, vp);

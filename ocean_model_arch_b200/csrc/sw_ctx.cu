@@ -402,6 +402,7 @@ int step_fused(swcu_ctx *c, double tau)
         int ex = 0;
         const double mant = frexp(tau, &ex);
         a.tau.tau = tau; a.tau.rtau = 1.0 / tau; a.tau.pow2 = (mant == 0.5 && tau > 1e-300 && tau < 1e300) ? 1 : 0;
+        a.tau.exact = 1;
     }
     a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
     a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;

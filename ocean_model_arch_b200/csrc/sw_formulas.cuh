@@ -40,7 +40,15 @@ __device__ __forceinline__ bool on(float mask) { return mask > 0.5f; }
 // c = flat index of the cell, r = its row (n - by1).  Neighbours: (m+-1) -> (c+-1, r),
 // (n+-1) -> (c+-p, r+-1).
 struct MetGen {
+    static constexpr bool kRecip = false;  // no reciprocal tables: divisions stay hardware divisions
     const float *dx_, *dy_, *dxt_, *dyt_, *dxh_, *dyh_, *dxb_, *dyb_, *rlh_;
+    __device__ __forceinline__ double r_dxt(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_dyt(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_dxh(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_dyh(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_dxb(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_dyb(long, int) const { return 0.0; }
+    __device__ __forceinline__ double r_area(long, int) const { return 0.0; }
     __device__ __forceinline__ double dx(long c, int) const { return (double)dx_[c]; }
     __device__ __forceinline__ double dy(long c, int) const { return (double)dy_[c]; }
     __device__ __forceinline__ double dxt(long c, int) const { return (double)dxt_[c]; }
@@ -64,10 +72,13 @@ struct MetGen {
 
 enum MetTab : int {
     T_DX, T_DY, T_DXT, T_DYT, T_DXH, T_DYH, T_DXB, T_DYB, T_RLH,
-    T_AREA, T_DY2, T_DX2, T_DXB2, T_DYB2, T_RYX, T_RXY, T_RXYB, T_RYXB, T_COUNT
+    T_AREA, T_DY2, T_DX2, T_DXB2, T_DYB2, T_RYX, T_RXY, T_RXYB, T_RYXB,
+    // correctly rounded reciprocals (1.0 / value, IEEE division) of the divisors the step uses
+    T_RDXT, T_RDYT, T_RDXH, T_RDYH, T_RDXB, T_RDYB, T_RAREA, T_COUNT
 };
 
 struct MetRow {
+    static constexpr bool kRecip = true;
     const double *tab;  // [T_COUNT][h]: global tables, or a shared-memory copy of rows r0 .. r0+h-1
     int h;
     int r0;
@@ -78,8 +89,45 @@ struct MetRow {
     SWCU_ROW(rlh, T_RLH) SWCU_ROW(area, T_AREA) SWCU_ROW(dy2, T_DY2) SWCU_ROW(dx2, T_DX2)
     SWCU_ROW(dxb2, T_DXB2) SWCU_ROW(dyb2, T_DYB2) SWCU_ROW(ryx, T_RYX) SWCU_ROW(rxy, T_RXY)
     SWCU_ROW(rxyb, T_RXYB) SWCU_ROW(ryxb, T_RYXB)
+    SWCU_ROW(r_dxt, T_RDXT) SWCU_ROW(r_dyt, T_RDYT) SWCU_ROW(r_dxh, T_RDXH) SWCU_ROW(r_dyh, T_RDYH)
+    SWCU_ROW(r_dxb, T_RDXB) SWCU_ROW(r_dyb, T_RDYB) SWCU_ROW(r_area, T_RAREA)
 #undef SWCU_ROW
 };
+
+// ---- exact division by a tabulated divisor ------------------------------------------------------
+// Correctly rounded a/b from y = RN(1/b) without the hardware division sequence (MUFU.RCP64H on the
+// slow XU pipe + ~8 dependent DFMA + range checks).  q0 = RN(a*y) is within 2 ulp of a/b; one
+// residual correction makes q1 faithful (error <= 1/2 ulp + 2^-104 relative); Markstein's theorem
+// (y the correctly rounded reciprocal, q1 faithful, r1 = a - b*q1 exact in one FMA) then gives
+// RN(q1 + r1*y) = RN(a/b), i.e. the same bits as the IEEE division the reference performs.
+// Valid for normal-range operands (every quantity of this model); a == 0 (and underflow) returns the
+// correctly signed zero q0.  Explicit fma() is used on purpose: -fmad=false only forbids implicit
+// contraction.
+__device__ __forceinline__ double mdiv(double a, double b, double y)
+{
+    const double q0 = a * y;
+    const double r0 = fma(-b, q0, a);
+    const double q1 = fma(r0, y, q0);
+    const double r1 = fma(-b, q1, a);
+    const double q = fma(r1, y, q1);
+    return q0 == 0.0 ? q0 : q;
+}
+template <class M>
+__device__ __forceinline__ double dv(double a, double b, double y)
+{
+    if constexpr (M::kRecip) return mdiv(a, b, y);
+    else return a / b;
+}
+
+// x / slu for slu = dble(lu+lu[+lu+lu]) with 0/1 masks, nsea = number of sea cells among them.
+// Division by 1, 2, 4 is an exact scaling, so multiplying by the exact reciprocal gives the same
+// bits as the reference's division; 3 goes through mdiv with RN(1/3).  (nsea = 0 only on masked-out
+// cells.)
+__device__ __forceinline__ double div_slu(double x, int nsea)
+{
+    if (nsea == 3) return mdiv(x, 3.0, 1.0 / 3.0);
+    return x * (nsea == 2 ? 0.5 : (nsea == 4 ? 0.25 : 1.0));
+}
 
 // ---- formulas -----------------------------------------------------------------------------------
 
@@ -92,7 +140,7 @@ __device__ __forceinline__ double f_sshn(long c, int r, int p, double tau, const
     const long w = c - 1, s = c - p;
     const double div = u[c] * hhu[c] * m.dyh(c, r) - u[w] * hhu[w] * m.dyh(w, r)
                      + v[c] * hhv[c] * m.dxh(c, r) - v[s] * hhv[s] * m.dxh(s, r - 1);
-    return sshp[c] + 2.0 * tau * (-(div / m.area(c, r)));
+    return sshp[c] + 2.0 * tau * (-dv<M>(div, m.area(c, r), m.r_area(c, r)));
 }
 
 // kernel/shallow_water/depth.f90:59-61 (and :70-72 with the +y neighbour).  lu_* are the real(4)
@@ -104,27 +152,22 @@ __device__ __forceinline__ double f_interp2(double hq_c, double hq_e,
     return (hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e) / slu / d1 / d2;
 }
 
-// x / slu for slu = dble(lu+lu[+lu+lu]) with 0/1 masks, nsea = number of sea cells among them.
-// Division by 1, 2, 4 is an exact scaling, so multiplying by the exact reciprocal gives the same
-// bits as the reference's division; 3 keeps the true division.  (nsea = 0 only on masked-out cells.)
-__device__ __forceinline__ double div_slu(double x, int nsea)
-{
-    if (nsea == 3) return x / 3.0;
-    return x * (nsea == 2 ? 0.5 : (nsea == 4 ? 0.25 : 1.0));
-}
-
 // f_interp2 / f_interp4 for masks known to be exactly 0 or 1 (fused path: masks come from bits)
+template <class M>
 __device__ __forceinline__ double f_interp2_b(double hq_c, double hq_e,
-        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e, int nsea, double d1, double d2)
+        double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e, int nsea,
+        double d1, double rd1, double d2, double rd2)
 {
-    return div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e, nsea) / d1 / d2;
+    return dv<M>(dv<M>(div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e, nsea), d1, rd1), d2, rd2);
 }
+template <class M>
 __device__ __forceinline__ double f_interp4_b(double hq_c, double hq_e, double hq_n, double hq_en,
         double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e,
-        double dx_n, double dy_n, double lu_n, double dx_en, double dy_en, double lu_en, int nsea, double dxb, double dyb)
+        double dx_n, double dy_n, double lu_n, double dx_en, double dy_en, double lu_en, int nsea,
+        double dxb, double rdxb, double dyb, double rdyb)
 {
-    return div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e
-                 + hq_n * dx_n * dy_n * lu_n + hq_en * dx_en * dy_en * lu_en, nsea) / dxb / dyb;
+    return dv<M>(dv<M>(div_slu(hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e
+                             + hq_n * dx_n * dy_n * lu_n + hq_en * dx_en * dy_en * lu_en, nsea), dxb, rdxb), dyb, rdyb);
 }
 
 // kernel/shallow_water/depth.f90:81-85
@@ -154,8 +197,8 @@ __device__ __forceinline__ double f_str_t(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v)
 {
     const long w = c - 1, s = c - p;
-    return m.ryx(c, r) * (u[c] / m.dyh(c, r) - u[w] / m.dyh(w, r))
-         - m.rxy(c, r) * (v[c] / m.dxh(c, r) - v[s] / m.dxh(s, r - 1));
+    return m.ryx(c, r) * (dv<M>(u[c], m.dyh(c, r), m.r_dyh(c, r)) - dv<M>(u[w], m.dyh(w, r), m.r_dyh(w, r)))
+         - m.rxy(c, r) * (dv<M>(v[c], m.dxh(c, r), m.r_dxh(c, r)) - dv<M>(v[s], m.dxh(s, r - 1), m.r_dxh(s, r - 1)));
 }
 
 // kernel/shallow_water/mixing.f90:50-51
@@ -164,8 +207,8 @@ __device__ __forceinline__ double f_str_s(long c, int r, int p, const M &m,
         const double *__restrict__ u, const double *__restrict__ v)
 {
     const long e = c + 1, no = c + p;
-    return m.rxyb(c, r) * (u[no] / m.dxt(no, r + 1) - u[c] / m.dxt(c, r))
-         + m.ryxb(c, r) * (v[e] / m.dyt(e, r) - v[c] / m.dyt(c, r));
+    return m.rxyb(c, r) * (dv<M>(u[no], m.dxt(no, r + 1), m.r_dxt(no, r + 1)) - dv<M>(u[c], m.dxt(c, r), m.r_dxt(c, r)))
+         + m.ryxb(c, r) * (dv<M>(v[e], m.dyt(e, r), m.r_dyt(e, r)) - dv<M>(v[c], m.dyt(c, r), m.r_dyt(c, r)));
 }
 
 // kernel/shallow_water/vel_ssh.f90:326-340 ; luu_c / luu_s = dble(luu(m,n)) / dble(luu(m,n-1))
@@ -207,8 +250,9 @@ __device__ __forceinline__ double f_rhsx_dif(long c, int r, int p, const M &m, d
     const long e = c + 1, no = c + p, s = c - p, en = c + 1 + p, es = c + 1 - p;
     const double muh_p = (mu[c] + mu[e] + mu[no] + mu[en]) / 4.0;
     const double muh_m = (mu[c] + mu[e] + mu[s] + mu[es]) / 4.0;
-    return (m.dy2(e, r) * mu[e] * hq_e * str_t[e] - m.dy2(c, r) * mu[c] * hq_c * str_t[c]) / m.dyh(c, r)
-         + (m.dxb2(c, r) * muh_p * hh[c] * str_s[c] - m.dxb2(s, r - 1) * muh_m * hh[s] * str_s[s]) / m.dxt(c, r);
+    return dv<M>(m.dy2(e, r) * mu[e] * hq_e * str_t[e] - m.dy2(c, r) * mu[c] * hq_c * str_t[c], m.dyh(c, r), m.r_dyh(c, r))
+         + dv<M>(m.dxb2(c, r) * muh_p * hh[c] * str_s[c] - m.dxb2(s, r - 1) * muh_m * hh[s] * str_s[s],
+                 m.dxt(c, r), m.r_dxt(c, r));
 }
 
 // kernel/shallow_water/vel_ssh.f90:438-444 ; hq_c / hq_n are hq(m,n) / hq(m,n+1)
@@ -220,16 +264,23 @@ __device__ __forceinline__ double f_rhsy_dif(long c, int r, int p, const M &m, d
     const long e = c + 1, w = c - 1, no = c + p, en = c + 1 + p, wn = c - 1 + p;
     const double muh_p = (mu[c] + mu[e] + mu[no] + mu[en]) / 4.0;
     const double muh_m = (mu[c] + mu[w] + mu[no] + mu[wn]) / 4.0;
-    return -(m.dx2(no, r + 1) * mu[no] * hq_n * str_t[no] - m.dx2(c, r) * mu[c] * hq_c * str_t[c]) / m.dxh(c, r)
-         + (m.dyb2(c, r) * muh_p * hh[c] * str_s[c] - m.dyb2(w, r) * muh_m * hh[w] * str_s[w]) / m.dyt(c, r);
+    return -dv<M>(m.dx2(no, r + 1) * mu[no] * hq_n * str_t[no] - m.dx2(c, r) * mu[c] * hq_c * str_t[c],
+                  m.dxh(c, r), m.r_dxh(c, r))
+         + dv<M>(m.dyb2(c, r) * muh_p * hh[c] * str_s[c] - m.dyb2(w, r) * muh_m * hh[w] * str_s[w],
+                 m.dyt(c, r), m.r_dyt(c, r));
 }
 
 // x / tau.  When tau is a power of two the division is an exact scaling and x * (1/tau) gives the
-// same bits (the host checks frexp(tau) == 0.5 * 2^e); otherwise the true division is kept.
+// same bits (the host checks frexp(tau) == 0.5 * 2^e); otherwise mdiv with rtau = RN(1/tau) from the
+// host's IEEE division.  exact = 0 (Level A, which has no host-side setup) keeps the hardware division.
 struct Tau {
     double tau, rtau;
-    int pow2;
-    __device__ __forceinline__ double div(double x) const { return pow2 ? x * rtau : x / tau; }
+    int pow2, exact;
+    __device__ __forceinline__ double div(double x) const
+    {
+        if (pow2) return x * rtau;
+        return exact ? mdiv(x, tau, rtau) : x / tau;
+    }
 };
 
 // kernel/shallow_water/vel_ssh.f90:167-176 ; FreeFallAcc is real(4) 9.8 promoted;

@@ -307,6 +307,11 @@ __global__ void k_build_tables(Geo g, MetGen mg, double *__restrict__ tab, int h
     tab[T_DXB2 * h + r] = mg.dxb2(c, r); tab[T_DYB2 * h + r] = mg.dyb2(c, r);
     tab[T_RYX * h + r] = mg.ryx(c, r);   tab[T_RXY * h + r] = mg.rxy(c, r);
     tab[T_RXYB * h + r] = mg.rxyb(c, r); tab[T_RYXB * h + r] = mg.ryxb(c, r);
+    // correctly rounded reciprocals for mdiv() (IEEE division, done once per row)
+    tab[T_RDXT * h + r] = 1.0 / mg.dxt(c, r); tab[T_RDYT * h + r] = 1.0 / mg.dyt(c, r);
+    tab[T_RDXH * h + r] = 1.0 / mg.dxh(c, r); tab[T_RDYH * h + r] = 1.0 / mg.dyh(c, r);
+    tab[T_RDXB * h + r] = 1.0 / mg.dxb(c, r); tab[T_RDYB * h + r] = 1.0 / mg.dyb(c, r);
+    tab[T_RAREA * h + r] = 1.0 / mg.area(c, r);
 }
 
 // *nonrow += number of cells in columns [bx1+1 .. bx2-1] whose nine real(4) metric values differ

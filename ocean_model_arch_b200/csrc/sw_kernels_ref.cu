@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, double tau,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, dxt, dyt, dxh, dyh, dxb, dyb, rlh_s};
-    const Tau tt{tau, 0.0, 0};  // Level A always divides
+    const Tau tt{tau, 0.0, 0, 0};  // Level A always divides
     if (on(lcu[c]))
         un[c] = f_un(c, r, p, tt, mg, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
                      (double)(rdis[c] + rdis[c + 1]), hhh, ssh, v, up);
