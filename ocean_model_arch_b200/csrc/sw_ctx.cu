@@ -142,7 +142,7 @@ struct swcu_ctx {
     const float **arr_list_dev = nullptr;
     int *nonrow_dev = nullptr;
     bool want_tiled = true;                   // one-launch TMA-tiled step when the tables are usable
-    int tile_variant = 3;
+    int tile_variant = 4;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
     // per-launch event pairs, filled only inside swcu_profile_steps
     bool prof = false;

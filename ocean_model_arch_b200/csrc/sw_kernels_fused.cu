@@ -275,7 +275,7 @@ int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, in
         case 3: return step_dispatch<TileCfg<8, 1, 3>>(maps, g, a, n0, n1, st);
         case 4: return step_dispatch<TileCfg<8, 2, 4>>(maps, g, a, n0, n1, st);
         case 5: return step_dispatch<TileCfg<16, 4, 2>>(maps, g, a, n0, n1, st);
-        default: return step_dispatch<TileCfg<8, 1, 3>>(maps, g, a, n0, n1, st);
+        default: return step_dispatch<TileCfg<8, 2, 4>>(maps, g, a, n0, n1, st);
     }
 }
 
