@@ -122,4 +122,89 @@ __device__ __forceinline__ UpdOut update_cell(long c, int r, int p, const M &mt,
     return o;
 }
 
+// ---- tracer step (control/tracer.f90:44-61) fused into one cell function ------------------------
+// hhu/hhv at the NEW time level (what K10 left in grid_data%hhu / %hhv when expl_tracer runs),
+// re-evaluated from the resident state like stage A does.
+template <class M>
+__device__ __forceinline__ double depth_u(long c, int r, const M &mt, double ffs, const unsigned char *__restrict__ mask,
+                                          const double *__restrict__ ssh, const double *__restrict__ h_r)
+{
+    const long e = c + 1;
+    const int b_c = mask[c] & MB_LU, b_e = mask[e] & MB_LU;
+    return f_interp2_b<M>(h_r[c] + ssh[c] * ffs, h_r[e] + ssh[e] * ffs, mt.dx(c, r), mt.dy(c, r), b_c ? 1.0 : 0.0,
+                          mt.dx(e, r), mt.dy(e, r), b_e ? 1.0 : 0.0, b_c + b_e,
+                          mt.dxt(c, r), mt.r_dxt(c, r), mt.dyh(c, r), mt.r_dyh(c, r));
+}
+template <class M>
+__device__ __forceinline__ double depth_v(long c, int r, int p, const M &mt, double ffs,
+                                          const unsigned char *__restrict__ mask,
+                                          const double *__restrict__ ssh, const double *__restrict__ h_r)
+{
+    const long no = c + p;
+    const int b_c = mask[c] & MB_LU, b_n = mask[no] & MB_LU;
+    return f_interp2_b<M>(h_r[c] + ssh[c] * ffs, h_r[no] + ssh[no] * ffs, mt.dx(c, r), mt.dy(c, r), b_c ? 1.0 : 0.0,
+                          mt.dx(no, r + 1), mt.dy(no, r + 1), b_n ? 1.0 : 0.0, b_c + b_n,
+                          mt.dxh(c, r), mt.r_dxh(c, r), mt.dyt(c, r), mt.r_dyt(c, r));
+}
+
+// kernel/tracer/leapfrog_tracer.f90:59-73: total zonal flux through the east face of cell c
+// (0 where lcu is off: the reference's flux array keeps its initial zero there)
+template <class M>
+__device__ __forceinline__ double tracer_flux_x(long c, int r, const M &mt, double ffs, double factor_mu,
+        const unsigned char *__restrict__ mask, const double *__restrict__ ssh, const double *__restrict__ h_r,
+        const double *__restrict__ uu, const double *__restrict__ mu, const double *__restrict__ ff)
+{
+    const long e = c + 1;
+    const double hhu = depth_u(c, r, mt, ffs, mask, ssh, h_r);
+    const double dfdx = ff[e] - ff[c];
+    const double mu_1d = dv<M>((mu[c] + mu[e]) / 2.0 * factor_mu * mt.dyh(c, r), mt.dxt(c, r), mt.r_dxt(c, r));
+    const double flux_diff = mu_1d * hhu * dfdx;
+    const double flux_adv = -uu[c] * hhu * mt.dyh(c, r) * (ff[c] + ff[e]) / 2.0;
+    const double f = flux_adv + flux_diff + 0.0;
+    return (mask[c] & MB_LCU) ? f : 0.0;
+}
+// kernel/tracer/leapfrog_tracer.f90:76-90
+template <class M>
+__device__ __forceinline__ double tracer_flux_y(long c, int r, int p, const M &mt, double ffs, double factor_mu,
+        const unsigned char *__restrict__ mask, const double *__restrict__ ssh, const double *__restrict__ h_r,
+        const double *__restrict__ vv, const double *__restrict__ mu, const double *__restrict__ ff)
+{
+    const long no = c + p;
+    const double hhv = depth_v(c, r, p, mt, ffs, mask, ssh, h_r);
+    const double dfdy = ff[no] - ff[c];
+    const double mu_1d = dv<M>((mu[c] + mu[no]) / 2.0 * factor_mu * mt.dxh(c, r), mt.dyt(c, r), mt.r_dyt(c, r));
+    const double flux_diff = mu_1d * hhv * dfdy;
+    const double flux_adv = -vv[c] * hhv * mt.dxh(c, r) * (ff[c] + ff[no]) / 2.0;
+    const double f = flux_adv + flux_diff + 0.0;
+    return (mask[c] & MB_LCV) ? f : 0.0;
+}
+
+struct TracerOut { double ff, ffp; };
+
+// tran_diff_fluxes + tran_diff_tracer + tracer_next_step for cell c (leapfrog_tracer.f90:13-170), with
+// hhq_n = hhq_rest and hhq_p = hhq_rest + sshp*ffs as K10 leaves them (depth.f90:48-50).
+// ssh, sshp, uu, vv are the state AFTER the shallow-water step of the same model step.
+template <class M>
+__device__ __forceinline__ TracerOut tracer_cell(long c, int r, int p, const M &mt, const Tau &tau, double ts, double ffs,
+        const unsigned char *__restrict__ mask, const double *__restrict__ ssh, const double *__restrict__ sshp,
+        const double *__restrict__ h_r, const double *__restrict__ uu, const double *__restrict__ vv,
+        const double *__restrict__ mu, const double *__restrict__ ff, const double *__restrict__ ffp)
+{
+    const double fx_c = tracer_flux_x(c, r, mt, ffs, 1.0, mask, ssh, h_r, uu, mu, ff);
+    const double fx_w = tracer_flux_x(c - 1, r, mt, ffs, 1.0, mask, ssh, h_r, uu, mu, ff);
+    const double fy_c = tracer_flux_y(c, r, p, mt, ffs, 1.0, mask, ssh, h_r, vv, mu, ff);
+    const double fy_s = tracer_flux_y(c - p, r - 1, p, mt, ffs, 1.0, mask, ssh, h_r, vv, mu, ff);
+    const double dx = mt.dx(c, r), dy = mt.dy(c, r);
+    const double bp = tau.div(h_r[c] * dx * dy) / 2.0;                          // leapfrog_tracer.f90:128
+    const double bp0 = tau.div((h_r[c] + sshp[c] * ffs) * dx * dy) / 2.0;       // :129
+    const double rhs = fx_c - fx_w + fy_c - fy_s;
+    const double eta = bp0 * ffp[c] + rhs;
+    const double ffn = eta / bp;
+    const bool sea = mask[c] & MB_LU;
+    TracerOut o;
+    o.ffp = sea ? f_filter(ff[c], ffn, ffp[c], ts) : ffp[c];                    // :163-164
+    o.ff = sea ? ffn : ff[c];
+    return o;
+}
+
 }  // namespace swcu

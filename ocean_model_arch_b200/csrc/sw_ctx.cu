@@ -126,6 +126,7 @@ struct swcu_ctx {
     double *f8[SWCU_NF8] = {};
     float *f4[SWCU_NF4] = {};
     double *alt[6] = {};  // FUSED: second copy of the prognostic arrays (ping-pong)
+    double *alt_ff[2] = {};  // FUSED + tracers: second copy of ff1, ff1p
     unsigned char *mask = nullptr;
     bool alt_dirty = true;
     bool has_rhs = false, has_rdiss = false;
@@ -386,6 +387,10 @@ int step_fused(swcu_ctx *c, double tau)
         for (int i = 0; i < 6; ++i)
             SWCU_CUDA(cudaMemcpyAsync(c->alt[i], c->f8[kState[i]], c->plane * sizeof(double),
                                       cudaMemcpyDeviceToDevice, c->st));
+        if (c->p.use_tracers) {
+            SWCU_CUDA(cudaMemcpyAsync(c->alt_ff[0], c->f8[SWCU_F_FF1], c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            SWCU_CUDA(cudaMemcpyAsync(c->alt_ff[1], c->f8[SWCU_F_FF1P], c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        }
         c->alt_dirty = false;
     }
     FusedArgs a;
@@ -406,6 +411,10 @@ int step_fused(swcu_ctx *c, double tau)
     }
     a.ts = c->p.time_smooth; a.ffs = (double)c->p.full_free_surface;
     a.trans = c->p.trans_terms > 0; a.lat = c->p.ksw_lat > 0;
+    a.ff = a.ffp = nullptr; a.ff_o = a.ffp_o = nullptr;
+    if (c->p.use_tracers) {
+        a.ff = c->f8[SWCU_F_FF1]; a.ffp = c->f8[SWCU_F_FF1P]; a.ff_o = c->alt_ff[0]; a.ffp_o = c->alt_ff[1];
+    }
 
     const int ns = g.ny_start, ne = g.ny_end;
     const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(a);
@@ -443,6 +452,22 @@ int step_fused(swcu_ctx *c, double tau)
         RC(rows(i0, i1));
         SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
     }
+    if (c->p.use_tracers) {
+        // expl_tracer (control/tracer.f90:44-61) on the state just written (and, with a communicator,
+        // just exchanged: the compute stream already waits on the exchange event)
+        RC(launch_tracer(g, a, ns, ne, c->st));
+        c->launches++;
+        if (c->comm) {
+            SWCU_NCCL(g_nccl.GroupStart());
+            int rc = exchange_rows(c, c->alt_ff[0], 2, c->st);
+            if (!rc) rc = exchange_rows(c, c->alt_ff[1], 2, c->st);
+            ncclResult_t r = g_nccl.GroupEnd();
+            if (rc) return rc;
+            if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+        }
+        double *t = c->f8[SWCU_F_FF1]; c->f8[SWCU_F_FF1] = c->alt_ff[0]; c->alt_ff[0] = t;
+        t = c->f8[SWCU_F_FF1P]; c->f8[SWCU_F_FF1P] = c->alt_ff[1]; c->alt_ff[1] = t;
+    }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
     return SWCU_OK;
 }
@@ -474,9 +499,10 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
             c->has_rhs = true;  // the reference never assigns RHSx/RHSy; first upload makes them resident
             RC(alloc8(c, SWCU_F_RHSX)); RC(alloc8(c, SWCU_F_RHSY));
         }
+        if (fused && is_tracer_field(field) && field != SWCU_F_FF1 && field != SWCU_F_FF1P) return SWCU_OK;
         if (fused && !fused_keeps8(c, field) && !is_tracer_field(field)) return SWCU_OK;  // derived: recomputed on device
         RC(copy_in(c, c->f8[field], (const double *)src, kind));
-        if (fused && state_slot(field) >= 0) c->alt_dirty = true;
+        if (fused && (state_slot(field) >= 0 || is_tracer_field(field))) c->alt_dirty = true;
         return SWCU_OK;
     }
     if (is_f4(field)) {
@@ -515,7 +541,8 @@ int download_impl(swcu_ctx *c, int field, void *dst, bool to_device)
             if (field == SWCU_F_SSHN) src = c->f8[SWCU_F_SSH];
             else if (field == SWCU_F_UBRTRN) src = c->f8[SWCU_F_UBRTR];
             else if (field == SWCU_F_VBRTRN) src = c->f8[SWCU_F_VBRTR];
-            else if (!fused_keeps8(c, field) && !(is_tracer_field(field) && c->p.use_tracers)) {
+            else if (field == SWCU_F_FF1N && c->p.use_tracers) src = c->f8[SWCU_F_FF1];
+            else if (!fused_keeps8(c, field) && !((field == SWCU_F_FF1 || field == SWCU_F_FF1P) && c->p.use_tracers)) {
                 set_error("field %d is not resident in FUSED mode", field);
                 return SWCU_ERR_STATE;
             }
@@ -554,10 +581,6 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
     if (!out || !params) { set_error("null argument"); return SWCU_ERR_ARG; }
     RC(check_dims(dims));
     if (params->mode != SWCU_MODE_REFERENCE && params->mode != SWCU_MODE_FUSED) { set_error("bad mode"); return SWCU_ERR_ARG; }
-    if (params->mode == SWCU_MODE_FUSED && params->use_tracers) {
-        set_error("tracers need SWCU_MODE_REFERENCE in this version");
-        return SWCU_ERR_STATE;
-    }
     int ndev = 0;
     SWCU_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("device %d of %d", device, ndev); return SWCU_ERR_ARG; }
@@ -593,6 +616,10 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
     } else {
         for (int f = 0; f < SWCU_NF8; ++f) if (fused_keeps8(c, f)) TRY(alloc8(c, f));
         for (int i = 0; i < 6; ++i) TRY(dev_alloc(c, (void **)&c->alt[i], c->plane * sizeof(double)));
+        if (params->use_tracers) {
+            TRY(alloc8(c, SWCU_F_FF1)); TRY(alloc8(c, SWCU_F_FF1P));
+            for (int i = 0; i < 2; ++i) TRY(dev_alloc(c, (void **)&c->alt_ff[i], c->plane * sizeof(double)));
+        }
         for (int f = 100; f < SWCU_F4_END; ++f) if (fused_keeps4(c, f)) TRY(alloc4(c, f));
         TRY(dev_alloc(c, (void **)&c->mask, c->plane));
     }
@@ -611,6 +638,7 @@ int swcu_destroy(swcu_ctx *c)
     for (auto &p : c->f8) cudaFree(p);
     for (auto &p : c->f4) cudaFree(p);
     for (auto &p : c->alt) cudaFree(p);
+    for (auto &p : c->alt_ff) cudaFree(p);
     cudaFree(c->mask); cudaFree(c->bad_dev);
     cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev);
     if (c->bad_host) cudaFreeHost(c->bad_host);

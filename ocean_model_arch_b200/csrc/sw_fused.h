@@ -29,6 +29,9 @@ struct FusedArgs {
     Tau tau;
     double ts, ffs;
     int trans, lat;
+    // tracer (ff1): level-n arrays read, n+1 written (ping-pong); nullptr without tracers
+    const double *ff, *ffp;
+    double *ff_o, *ffp_o;
 };
 
 // prep on rows [n0..n1] (columns nx_start-1 .. nx_end+1); update on rows [n0..n1] (columns of S)
@@ -43,6 +46,8 @@ void step_tile_box(int variant, int *box_w, int *box_h);
 // *nonrow_dev) the cells whose values differ from their row's entry.
 int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, int *nonrow_dev,
                         const float *const *arr_list_dev, cudaStream_t st);
+// expl_tracer for rows [n0..n1] in one launch; reads a.ssh_o .. a.v_o (the state the step just wrote)
+int launch_tracer(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 

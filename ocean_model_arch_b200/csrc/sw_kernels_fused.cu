@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(BX *BY) k_update(Geo g, FusedArgs a, int n0, i
     if (o.bad) atomicAdd(a.bad, 1);  // K11
 }
 
+// ---- tracer: fluxes + update + filter in one launch (after the step, on the n+1 state) ----------
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_tracer(Geo g, FusedArgs a, int n0, int n1)
+{
+    const int m = g.nx_start + blockIdx.x * BX + threadIdx.x;
+    const int n = n0 + blockIdx.y * BY + threadIdx.y;
+    if (m > g.nx_end || n > n1) return;
+    const long c = ix(g, m, n);
+    const typename MetOf<ROW>::type mt = MetOf<ROW>::make(a);
+    const TracerOut o = tracer_cell(c, n - g.by1, g.pitch, mt, a.tau, a.ts, a.ffs, a.mask, a.ssh_o, a.sshp_o, a.h_r,
+                                    a.u_o, a.v_o, a.mu, a.ff, a.ffp);
+    a.ff_o[c] = o.ff; a.ffp_o[c] = o.ffp;
+}
+
 // ---- one-launch path: TMA-staged shared-memory tiles, stages A and B in one kernel --------------
 // A CTA owns TX x TY output cells.  One thread issues eight cp.async.bulk.tensor.2d loads (ssh,
 // sshp, u, up, v, vp, hhq_rest, mu; box = tile + 2-cell halo, out-of-array cells zero-filled) that
@@ -234,6 +248,16 @@ int launch_update(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t
     if (a.tab) update_dispatch<true>(g, a, n0, n1, grid, block, st);
     else update_dispatch<false>(g, a, n0, n1, grid, block, st);
     return launched("update");
+}
+
+int launch_tracer(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st)
+{
+    if (n1 < n0) return SWCU_OK;
+    const dim3 block(BX, BY, 1);
+    const dim3 grid((unsigned)((g.nx_end - g.nx_start + BX) / BX), (unsigned)((n1 - n0 + BY) / BY), 1);
+    if (a.tab) k_tracer<true><<<grid, block, 0, st>>>(g, a, n0, n1);
+    else k_tracer<false><<<grid, block, 0, st>>>(g, a, n0, n1);
+    return launched("tracer");
 }
 
 namespace {

@@ -198,3 +198,21 @@ def test_time_steps_pow2_and_not(swlib, cuda_device, dt):
         m.step(25)
         for f in STATE:
             assert np.array_equal(m.get(f), o.get(f)), (f, dt, mode)
+
+
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_FUSED])
+@pytest.mark.parametrize("keep_mu", [False, True])
+def test_tracer_transport(swlib, cuda_device, mode, keep_mu):
+    """expl_tracer (control/tracer.f90:33-62, BASELINE config 5): ff1 / ff1p bitwise vs the oracle, with
+    the shipped mu = 0 (pure advection) and with mu = lvisc_2 (advection + diffusion)."""
+    nx, ny = 92, 71
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, use_tracers=1, keep_mu=int(keep_mu)), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), model.SwPar(use_tracers=1), mask=mask, mode=mode,
+                                keep_mu=keep_mu)
+    for steps in (1, 30):
+        o.step(steps); m.step(steps)
+        for f in STATE + ("ff1", "ff1p"):
+            assert np.array_equal(m.get(f), o.get(f)), (f, steps, mode)
+    ff = m.get("ff1")
+    assert ff.max() > 0.5 and not ff[mask == 1].any()
