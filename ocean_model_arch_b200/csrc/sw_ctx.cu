@@ -487,6 +487,68 @@ int copy_out(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
     return SWCU_OK;
 }
 
+// FUSED mode keeps no derived arrays.  For swcu_download they are rebuilt with the 1:1 kernels from the
+// resident state into scratch planes: the depth fields from the current state (what K10 left), and
+// vort / str_* / RHS*_adv / RHS*_dif from the PREVIOUS state, which the ping-pong buffers still hold
+// (what K3..K6 of the last step computed).  Before the first step those five are zero, like the
+// reference's fresh allocations.
+int materialize(swcu_ctx *c, int field, double **out_plane, std::vector<void *> &scratch)
+{
+    auto plane8 = [&](double **p) -> int {
+        SWCU_CUDA(cudaMalloc((void **)p, c->plane * sizeof(double)));
+        scratch.push_back(*p);
+        SWCU_CUDA(cudaMemsetAsync(*p, 0, c->plane * sizeof(double), c->st));
+        return SWCU_OK;
+    };
+    float *mk[7];
+    const int bits[7] = {MB_LU, MB_LUU, MB_LUH, MB_LCU, MB_LCV, MB_LLU, MB_LLV};
+    for (int i = 0; i < 7; ++i) {
+        SWCU_CUDA(cudaMalloc((void **)&mk[i], c->plane * sizeof(float)));
+        scratch.push_back(mk[i]);
+        RC(launch_mask_get((long)c->plane, mk[i], c->mask, bits[i], c->st));
+    }
+    float *lu = mk[0], *luu = mk[1], *luh = mk[2], *lcu = mk[3], *lcv = mk[4], *llu = mk[5], *llv = mk[6];
+    float *dx = F4(c, SWCU_F_DX), *dy = F4(c, SWCU_F_DY), *dxt = F4(c, SWCU_F_DXT), *dyt = F4(c, SWCU_F_DYT),
+          *dxh = F4(c, SWCU_F_DXH), *dyh = F4(c, SWCU_F_DYH), *dxb = F4(c, SWCU_F_DXB), *dyb = F4(c, SWCU_F_DYB);
+    const bool depth = field >= SWCU_F_HHQ && field <= SWCU_F_HHH_N;
+    const bool prev = !depth;
+    if (prev && c->steps_done == 0) { RC(plane8(out_plane)); return SWCU_OK; }
+    // state the requested field derives from
+    const double *ssh = prev ? c->alt[0] : c->f8[SWCU_F_SSH], *sshp = prev ? c->alt[1] : c->f8[SWCU_F_SSHP];
+    const double *u = prev ? c->alt[2] : c->f8[SWCU_F_UBRTR], *up = prev ? c->alt[3] : c->f8[SWCU_F_UBRTRP];
+    const double *v = prev ? c->alt[4] : c->f8[SWCU_F_VBRTR], *vp = prev ? c->alt[5] : c->f8[SWCU_F_VBRTRP];
+    double *hh[12];  // hq hqp hqn hu hup hun hv hvp hvn hh hhp hhn
+    for (auto &p : hh) RC(plane8(&p));
+    RC(launch_hh_init(c->g, c->p.full_free_surface, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                      hh[0], hh[1], hh[2], hh[3], hh[4], hh[5], hh[6], hh[7], hh[8], hh[9], hh[10], hh[11],
+                      ssh, sshp, c->f8[SWCU_F_HHQ_REST], c->st));
+    if (depth) { *out_plane = hh[field - SWCU_F_HHQ]; return SWCU_OK; }
+    double *vort, *str_t, *str_s, *ox, *oy;
+    RC(plane8(&vort)); RC(plane8(&str_t)); RC(plane8(&str_s)); RC(plane8(&ox)); RC(plane8(&oy));
+    if (c->p.trans_terms > 0) RC(launch_uv_trans_vort(c->g, luu, dxt, dyt, dxb, dyb, u, v, vort, c->st));
+    if (c->p.ksw_lat > 0)
+        RC(launch_stress_components(c->g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, up, vp, str_t, str_s, c->st));
+    switch (field) {
+        case SWCU_F_VORT: *out_plane = vort; return SWCU_OK;
+        case SWCU_F_STR_T: *out_plane = str_t; return SWCU_OK;
+        case SWCU_F_STR_S: *out_plane = str_s; return SWCU_OK;
+        case SWCU_F_RHSX_ADV: case SWCU_F_RHSY_ADV:
+            if (c->p.trans_terms > 0)
+                RC(launch_uv_trans(c->g, lcu, lcv, luu, dxh, dyh, u, v, vort, hh[3], hh[6], hh[9], ox, oy, c->st));
+            *out_plane = field == SWCU_F_RHSX_ADV ? ox : oy;
+            return SWCU_OK;
+        case SWCU_F_RHSX_DIF: case SWCU_F_RHSY_DIF:
+            if (c->p.ksw_lat > 0)
+                RC(launch_uv_diff2(c->g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, c->f8[SWCU_F_MU], str_t, str_s,
+                                   hh[0], hh[9], ox, oy, c->st));
+            *out_plane = field == SWCU_F_RHSX_DIF ? ox : oy;
+            return SWCU_OK;
+        default: break;
+    }
+    set_error("field %d cannot be materialised", field);
+    return SWCU_ERR_STATE;
+}
+
 int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
 {
     if (!c || !src) { set_error("null argument"); return SWCU_ERR_ARG; }
@@ -542,7 +604,16 @@ int download_impl(swcu_ctx *c, int field, void *dst, bool to_device)
             else if (field == SWCU_F_UBRTRN) src = c->f8[SWCU_F_UBRTR];
             else if (field == SWCU_F_VBRTRN) src = c->f8[SWCU_F_VBRTR];
             else if (field == SWCU_F_FF1N && c->p.use_tracers) src = c->f8[SWCU_F_FF1];
-            else if (!fused_keeps8(c, field) && !((field == SWCU_F_FF1 || field == SWCU_F_FF1P) && c->p.use_tracers)) {
+            else if ((field >= SWCU_F_HHQ && field <= SWCU_F_HHH_N) || field == SWCU_F_VORT || field == SWCU_F_STR_T ||
+                     field == SWCU_F_STR_S || (field >= SWCU_F_RHSX_ADV && field <= SWCU_F_RHSY_DIF)) {
+                std::vector<void *> scratch;
+                double *plane = nullptr;
+                rc = materialize(c, field, &plane, scratch);
+                if (!rc) rc = copy_out(c, (double *)dst, plane, kind);
+                cudaStreamSynchronize(c->st);
+                for (void *p : scratch) cudaFree(p);
+                return rc;
+            } else if (!fused_keeps8(c, field) && !((field == SWCU_F_FF1 || field == SWCU_F_FF1P) && c->p.use_tracers)) {
                 set_error("field %d is not resident in FUSED mode", field);
                 return SWCU_ERR_STATE;
             }
