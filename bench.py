@@ -149,9 +149,16 @@ def run_reference_arm(args, rank):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": f"synthetic rectangular basin {args.size}x{args.size} cells per GPU, flat 100 m bottom, "
-                        f"Gaussian SSH, full_free_surface=1 trans_terms=1 ksw_lat=1 (shipped sw.par), tau=1s",
-            "global_cells": [args.size, args.size * n_gpus], "decomposition": f"1x{n_gpus} y-slabs, one block per GPU",
+    gny = getattr(args, "global_ny", None) or args.size * n_gpus
+    extras = []
+    if getattr(args, "mask", "none") != "none": extras.append("synthetic land mask (LCG discs + sinusoidal coast, seed 20240229)")
+    if getattr(args, "keep_mu", False): extras.append("mu=lvisc_2=1e3")
+    if getattr(args, "r_diss", 0.0): extras.append(f"r_diss={args.r_diss}")
+    if getattr(args, "tracers", False): extras.append("use_tracers=1")
+    return {"workload": f"synthetic rectangular basin {args.size}x{gny // n_gpus} cells per GPU, flat 100 m bottom, "
+                        f"Gaussian SSH, full_free_surface=1 trans_terms=1 ksw_lat=1 (shipped sw.par), tau=1s"
+                        + ("; " + ", ".join(extras) if extras else ""),
+            "global_cells": [args.size, gny], "decomposition": f"1x{n_gpus} y-slabs, one block per GPU",
             "mode": args.mode, "l2": "working set > 126 MB L2 (12 ping-pong + 8 fp64 planes); no flush needed"
             if args.size >= 1536 else "working set may fit L2"}
 
@@ -168,6 +175,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tiled", action="store_true", help="fused mode: two launches per step instead of one")
     ap.add_argument("--tile-variant", type=int, default=None, help="tiled kernel variant (tuning)")
+    ap.add_argument("--global-ny", type=int, default=None,
+                    help="total computational rows over all GPUs (strong scaling); default size*gpus (weak)")
+    ap.add_argument("--mask", default="none", choices=["none", "islands"], help="synthetic land mask (config 3)")
+    ap.add_argument("--keep-mu", action="store_true", help="mu = lvisc_2 (lateral diffusion on, config 4)")
+    ap.add_argument("--r-diss", type=float, default=0.0, help="Rayleigh bottom friction 1/s (config 4: 5e-6)")
+    ap.add_argument("--tracers", action="store_true", help="use_tracers = 1 (config 5)")
+    ap.add_argument("--cartesian", action="store_true", help="curve_grid = 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -202,10 +216,17 @@ def main():
         dist.barrier()
 
     S = args.size
-    nx, ny = S + 4, S * world + 4
+    nx, ny = S + 4, (args.global_ny if args.global_ny else S * world) + 4
     mode = MODE_FUSED if args.mode == "fused" else MODE_REFERENCE
-    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=1 if ny < 20000 else 0)
-    m = model.ShallowWaterModel(bp, model.SwPar(), model.RunPar(), device=local_rank, mode=mode, rank=rank, world=world)
+    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=0 if (args.cartesian or ny >= 20000) else 1)
+    mask = None
+    if args.mask == "islands":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import basins
+        mask = basins.island_mask(nx, ny, ndisc=12)
+    m = model.ShallowWaterModel(bp, model.SwPar(use_tracers=1 if args.tracers else 0), model.RunPar(), mask=mask,
+                                device=local_rank, mode=mode, rank=rank, world=world, keep_mu=args.keep_mu,
+                                r_diss=args.r_diss, stripe_rows=1024 if nx * (ny // world) > 3000 * 3000 else None)
     if world > 1:
         ids = [model.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -201,6 +201,10 @@ int swcu_destroy(swcu_ctx *ctx);
  * number of steps. */
 int swcu_upload(swcu_ctx *ctx, int field, const void *host);
 int swcu_download(swcu_ctx *ctx, int field, void *host);
+/* Upload of `nrows` consecutive rows starting at 0-based array row `first_row` (reference row
+ * n = bnd_y1 + first_row); host points at nrows x (bnd_x2-bnd_x1+1) contiguous values.  Lets a host
+ * with less memory than the device stream a block in stripes. */
+int swcu_upload_rows(swcu_ctx *ctx, int field, const void *host, int first_row, int nrows);
 /* Same, but the other side is a DEVICE pointer in the reference layout (for callers that keep
  * their own device arrays, e.g. CUDA-Fortran field_device). */
 int swcu_upload_from_device(swcu_ctx *ctx, int field, const void *dev);

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "swcu_create": [C.POINTER(_P), _DIMS, C.POINTER(SwcuParams), _I],
     "swcu_destroy": [_P],
     "swcu_upload": [_P, _I, _P],
+    "swcu_upload_rows": [_P, _I, _P, _I, _I],
     "swcu_download": [_P, _I, _P],
     "swcu_upload_from_device": [_P, _I, _P],
     "swcu_download_to_device": [_P, _I, _P],

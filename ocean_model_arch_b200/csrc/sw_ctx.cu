@@ -480,6 +480,13 @@ int copy_in(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
     return SWCU_OK;
 }
 template <typename T>
+int copy_in_rows(swcu_ctx *c, T *dst, const T *src, int row0, int nrows, cudaMemcpyKind kind)
+{
+    SWCU_CUDA(cudaMemcpy2DAsync(dst + (size_t)row0 * c->pitch, (size_t)c->pitch * sizeof(T), src, (size_t)c->w * sizeof(T),
+                                (size_t)c->w * sizeof(T), (size_t)nrows, kind, c->st));
+    return SWCU_OK;
+}
+template <typename T>
 int copy_out(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
 {
     SWCU_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->w * sizeof(T), src, (size_t)c->pitch * sizeof(T),
@@ -549,9 +556,11 @@ int materialize(swcu_ctx *c, int field, double **out_plane, std::vector<void *> 
     return SWCU_ERR_STATE;
 }
 
-int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
+int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device, int row0 = 0, int nrows = -1)
 {
     if (!c || !src) { set_error("null argument"); return SWCU_ERR_ARG; }
+    if (nrows < 0) nrows = c->h;
+    if (row0 < 0 || nrows < 0 || row0 + nrows > c->h) { set_error("rows [%d, %d) outside the block (%d rows)", row0, row0 + nrows, c->h); return SWCU_ERR_ARG; }
     Use use(c->device);
     const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const bool fused = c->p.mode == SWCU_MODE_FUSED;
@@ -563,7 +572,7 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
         }
         if (fused && is_tracer_field(field) && field != SWCU_F_FF1 && field != SWCU_F_FF1P) return SWCU_OK;
         if (fused && !fused_keeps8(c, field) && !is_tracer_field(field)) return SWCU_OK;  // derived: recomputed on device
-        RC(copy_in(c, c->f8[field], (const double *)src, kind));
+        RC(copy_in_rows(c, c->f8[field], (const double *)src, row0, nrows, kind));
         if (fused && (state_slot(field) >= 0 || is_tracer_field(field))) c->alt_dirty = true;
         return SWCU_OK;
     }
@@ -572,10 +581,16 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
         if (fused && bit) {
             // stage through a scratch real(4) plane, then fold into the mask byte
             float *tmp = nullptr;
-            SWCU_CUDA(cudaMalloc((void **)&tmp, c->plane * sizeof(float)));
-            SWCU_CUDA(cudaMemsetAsync(tmp, 0, c->plane * sizeof(float), c->st));
-            int rc = copy_in(c, tmp, (const float *)src, kind);
-            if (!rc) rc = launch_mask_set((long)c->plane, tmp, c->mask, bit, c->st);
+            const size_t cnt = (size_t)nrows * c->pitch;
+            SWCU_CUDA(cudaMalloc((void **)&tmp, cnt * sizeof(float)));
+            SWCU_CUDA(cudaMemsetAsync(tmp, 0, cnt * sizeof(float), c->st));
+            int rc = SWCU_OK;
+            {
+                cudaError_t e = cudaMemcpy2DAsync(tmp, (size_t)c->pitch * sizeof(float), src, (size_t)c->w * sizeof(float),
+                                                  (size_t)c->w * sizeof(float), (size_t)nrows, kind, c->st);
+                if (e != cudaSuccess) rc = cuda_fail(e, "mask upload");
+            }
+            if (!rc) rc = launch_mask_set((long)cnt, tmp, c->mask + (size_t)row0 * c->pitch, bit, c->st);
             cudaStreamSynchronize(c->st);
             cudaFree(tmp);
             return rc;
@@ -583,7 +598,7 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device)
         if (fused && field == SWCU_F_R_DISS && !c->has_rdiss) { c->has_rdiss = true; RC(alloc4(c, SWCU_F_R_DISS)); }
         if (fused && !fused_keeps4(c, field)) return SWCU_OK;
         if (field >= SWCU_F_DX && field <= SWCU_F_RLH_S) c->metrics_dirty = true;
-        return copy_in(c, F4(c, field), (const float *)src, kind);
+        return copy_in_rows(c, F4(c, field), (const float *)src, row0, nrows, kind);
     }
     set_error("unknown field id %d", field);
     return SWCU_ERR_ARG;
@@ -725,6 +740,10 @@ int swcu_destroy(swcu_ctx *c)
 
 int swcu_upload(swcu_ctx *c, int field, const void *host) { return upload_impl(c, field, host, false); }
 int swcu_upload_from_device(swcu_ctx *c, int field, const void *dev) { return upload_impl(c, field, dev, true); }
+int swcu_upload_rows(swcu_ctx *c, int field, const void *host, int first_row, int nrows)
+{
+    return upload_impl(c, field, host, false, first_row, nrows);
+}
 int swcu_download(swcu_ctx *c, int field, void *host) { return download_impl(c, field, host, false); }
 int swcu_download_to_device(swcu_ctx *c, int field, void *dev) { return download_impl(c, field, dev, true); }
 

@@ -219,6 +219,33 @@ class DeviceBlock:
     def download_ptr(self, name, host_ptr):
         check(self.L.swcu_download(self.h, FIELD_ID[name], C.c_void_p(host_ptr)))
 
+    def upload_rows(self, name, arr, first_row):
+        want = np.float64 if name in F8_NAMES else np.float32
+        a = np.ascontiguousarray(arr, dtype=want)
+        assert a.shape[1] == self.dims.shape[1]
+        check(self.L.swcu_upload_rows(self.h, FIELD_ID[name], _ptr(a), int(first_row), int(a.shape[0])))
+        check(self.L.swcu_synchronize(self.h, None))
+
+    def upload_inputs_striped(self, basin, sw, mask=None, stripe_rows=512, **kw):
+        """Same result as upload_inputs(BlockInputs(...)) but built and uploaded `stripe_rows` array rows
+        at a time, so host memory stays bounded for blocks far larger than host RAM (16384^2 per GPU).
+        Arrays that are identically zero are not uploaded (device fields start zero-filled)."""
+        d = self.dims
+        h = d.shape[0]
+        for a in range(0, h, stripe_rows):
+            b = min(a + stripe_rows, h) - 1                      # upload array rows a..b
+            extra = 1 if b < h - 1 else 0                        # derived masks of row b need lu of row b+1
+            n1, n2 = d.bnd_y1 + a, d.bnd_y1 + b + extra
+            sd = SwcuDims(d.nx_start, d.nx_end, n1, n2, d.bnd_x1, d.bnd_x2, n1, n2)
+            inp = BlockInputs(basin, sw, sd, mask, **kw)
+            for name, arr in inp.f.items():
+                part = arr[:b - a + 1]
+                if name in ("sshn", "ubrtrn", "vbrtrn", "ff1n") or not part.any():
+                    continue
+                self.upload_rows(name, part, a)
+            del inp
+        self.hh_init()
+
     def upload_inputs(self, inp: BlockInputs):
         for name, arr in inp.f.items():
             if name == "r_diss" and not arr.any():
@@ -292,7 +319,8 @@ class ShallowWaterModel:
     y-slabs (parallel.par bppnx = 1, bppny = world size)."""
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, mask=None,
-                 device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0):
+                 device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0,
+                 stripe_rows=None):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
@@ -300,10 +328,15 @@ class ShallowWaterModel:
         if mask is None and self.basin.mask_file_name != "none":
             mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
         self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
-        self.inputs = BlockInputs(self.basin, self.sw, self.dims, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
-                                  r_diss=r_diss)
         self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode)
-        self.block.upload_inputs(self.inputs)
+        if stripe_rows:
+            self.inputs = None
+            self.block.upload_inputs_striped(self.basin, self.sw, mask, stripe_rows, hhq_rest=hhq_rest, keep_mu=keep_mu,
+                                             r_diss=r_diss)
+        else:
+            self.inputs = BlockInputs(self.basin, self.sw, self.dims, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
+                                      r_diss=r_diss)
+            self.block.upload_inputs(self.inputs)
         self.tau = self.run.tau
         self.num_step = 0
 

@@ -217,3 +217,19 @@ def test_tracer_transport(swlib, cuda_device, mode, keep_mu):
             assert np.array_equal(m.get(f), o.get(f)), (f, steps, mode)
     ff = m.get("ff1")
     assert ff.max() > 0.5 and not ff[mask == 1].any()
+
+
+def test_striped_upload_equals_whole_upload(swlib, cuda_device):
+    """Blocks larger than host memory are built and uploaded in row stripes (swcu_upload_rows); the
+    resident fields must be identical to a whole-block upload."""
+    nx, ny = 83, 131
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, r_diss=5e-6), mask)
+    kw = dict(mask=mask, mode=MODE_FUSED, keep_mu=True, r_diss=5e-6)
+    a = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), **kw)
+    b = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), stripe_rows=17, **kw)
+    for f in ("lu", "luu", "luh", "lcu", "lcv", "llu", "llv", "dx", "dyh", "rlh_s", "r_diss", "hhq_rest", "mu", "ssh"):
+        assert np.array_equal(a.get(f), b.get(f)), f
+    o.step(20); b.step(20)
+    for f in STATE:
+        assert np.array_equal(b.get(f), o.get(f)), f
