@@ -159,6 +159,7 @@ def workload_config(args, n_gpus):
                         f"Gaussian SSH, full_free_surface=1 trans_terms=1 ksw_lat=1 (shipped sw.par), tau=1s"
                         + ("; " + ", ".join(extras) if extras else ""),
             "global_cells": [args.size, gny], "decomposition": f"1x{n_gpus} y-slabs, one block per GPU",
+            "grid": "carthesian" if getattr(args, "curve_grid", 1) == 0 else "spherical (shipped basin.par)",
             "mode": args.mode, "l2": "working set > 126 MB L2 (12 ping-pong + 8 fp64 planes); no flush needed"
             if args.size >= 1536 else "working set may fit L2"}
 
@@ -218,7 +219,11 @@ def main():
     S = args.size
     nx, ny = S + 4, (args.global_ny if args.global_ny else S * world) + 4
     mode = MODE_FUSED if args.mode == "fused" else MODE_REFERENCE
-    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=0 if (args.cartesian or ny >= 20000) else 1)
+    # spherical metrics (shipped basin.par) while the basin stays below ~63N; beyond that dx = R cos(lat) dlon
+    # shrinks until tau = 1 s violates the CFL limit, so taller basins use the carthesian grid
+    curve_grid = 0 if (args.cartesian or ny > 8200) else 1
+    args.curve_grid = curve_grid
+    bp = model.BasinPar(nx=nx, ny=ny, curve_grid=curve_grid)
     mask = None
     if args.mask == "islands":
         sys.path.insert(0, os.path.join(ROOT, "tests"))
