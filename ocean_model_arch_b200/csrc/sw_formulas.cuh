@@ -100,9 +100,10 @@ struct MetRow {
 // residual correction makes q1 faithful (error <= 1/2 ulp + 2^-104 relative); Markstein's theorem
 // (y the correctly rounded reciprocal, q1 faithful, r1 = a - b*q1 exact in one FMA) then gives
 // RN(q1 + r1*y) = RN(a/b), i.e. the same bits as the IEEE division the reference performs.
-// Valid for normal-range operands (every quantity of this model); a == 0 (and underflow) returns the
-// correctly signed zero q0.  Explicit fma() is used on purpose: -fmad=false only forbids implicit
-// contraction.
+// Valid for normal-range operands (every quantity of this model).  The only case the FMA chain gets
+// wrong is the SIGN of a zero quotient (a = -0 gives +0); since sign(a/b) = sign(a*y) always, the sign
+// bit of q0 is copied onto the result (one LOP3).  Explicit fma() is used on purpose: -fmad=false only
+// forbids implicit contraction.
 __device__ __forceinline__ double mdiv(double a, double b, double y)
 {
     const double q0 = a * y;
@@ -110,7 +111,7 @@ __device__ __forceinline__ double mdiv(double a, double b, double y)
     const double q1 = fma(r0, y, q0);
     const double r1 = fma(-b, q1, a);
     const double q = fma(r1, y, q1);
-    return q0 == 0.0 ? q0 : q;
+    return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (__double2hiint(q0) & 0x80000000), __double2loint(q));
 }
 template <class M>
 __device__ __forceinline__ double dv(double a, double b, double y)
