@@ -121,8 +121,8 @@ struct swcu_ctx {
     Geo g;
     int pitch = 0, w = 0, h = 0;
     size_t plane = 0;  // pitch * h elements
-    cudaStream_t st = nullptr, comm_st = nullptr;
-    cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, t0 = nullptr, t1 = nullptr;
+    cudaStream_t st = nullptr, comm_st = nullptr, bnd_st = nullptr;
+    cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr, ev_start = nullptr, t0 = nullptr, t1 = nullptr;
     double *f8[SWCU_NF8] = {};
     float *f4[SWCU_NF4] = {};
     double *alt[6] = {};  // FUSED: second copy of the prognostic arrays (ping-pong)
@@ -233,12 +233,12 @@ int sync_fields(swcu_ctx *c, std::initializer_list<int> fields)
     return SWCU_OK;
 }
 
-int prof_mark(swcu_ctx *c, int kind, bool begin)
+int prof_mark(swcu_ctx *c, int kind, bool begin, cudaStream_t st = nullptr)
 {
     if (!c->prof) return SWCU_OK;
     cudaEvent_t e;
     SWCU_CUDA(cudaEventCreate(&e));
-    SWCU_CUDA(cudaEventRecord(e, c->st));
+    SWCU_CUDA(cudaEventRecord(e, st ? st : c->st));
     c->prof_ev.push_back(e);
     if (begin) c->prof_kind.push_back(kind);
     return SWCU_OK;
@@ -427,30 +427,35 @@ int step_fused(swcu_ctx *c, double tau)
         c->launches++;
     }
     // rows [r0..r1] of the n+1 state: one tiled launch, or the update stage of the two-launch path
-    auto rows = [&](int r0, int r1) -> int {
+    auto rows = [&](int r0, int r1, cudaStream_t st) -> int {
         if (r1 < r0) return SWCU_OK;
-        PROF(1, tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, c->st) : launch_update(g, a, r0, r1, c->st));
+        RC(prof_mark(c, 1, true, st));
+        RC(tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, st) : launch_update(g, a, r0, r1, st));
+        RC(prof_mark(c, 1, false, st));
         c->launches++;
         return SWCU_OK;
     };
     if (!c->comm) {
-        RC(rows(ns, ne));
+        RC(rows(ns, ne, c->st));
     } else {
-        // boundary strips (the two rows each neighbour needs) first, then the exchange on the side
-        // stream overlapped with the interior update
+        // The two boundary strips (the rows each neighbour needs) run on a high-priority stream
+        // concurrently with the interior update; their completion releases the NCCL exchange on a
+        // second high-priority stream, and the compute stream joins both before the next step.
         const bool lo = c->rank > 0, hi = c->rank + 1 < c->nranks;
         int i0 = ns, i1 = ne;
-        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(rows(ns, e)); i0 = e + 1; }
-        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(rows(s, ne)); i1 = s - 1; }
-        SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->st));
+        SWCU_CUDA(cudaEventRecord(c->ev_start, c->st));
+        SWCU_CUDA(cudaStreamWaitEvent(c->bnd_st, c->ev_start, 0));
+        if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(rows(ns, e, c->bnd_st)); i0 = e + 1; }
+        if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(rows(s, ne, c->bnd_st)); i1 = s - 1; }
+        SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->bnd_st));
         SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
         SWCU_NCCL(g_nccl.GroupStart());
         for (int i = 0; i < 6; ++i)
             if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
         SWCU_NCCL(g_nccl.GroupEnd());
         SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
-        RC(rows(i0, i1));
-        SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
+        RC(rows(i0, i1, c->st));
+        SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));  // strips -> exchange -> here
     }
     if (c->p.use_tracers) {
         // expl_tracer (control/tracer.f90:44-61) on the state just written (and, with a communicator,
@@ -686,9 +691,11 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
         int lo = 0, hi = 0;
         TRYCUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         TRYCUDA(cudaStreamCreateWithPriority(&c->comm_st, cudaStreamNonBlocking, hi));
+        TRYCUDA(cudaStreamCreateWithPriority(&c->bnd_st, cudaStreamNonBlocking, hi));
     }
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreate(&c->t0));
     TRYCUDA(cudaEventCreate(&c->t1));
     TRY(dev_alloc(c, (void **)&c->bad_dev, sizeof(int)));
@@ -730,6 +737,8 @@ int swcu_destroy(swcu_ctx *c)
     if (c->bad_host) cudaFreeHost(c->bad_host);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->bnd_st) cudaStreamDestroy(c->bnd_st);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->st) cudaStreamDestroy(c->st);
@@ -823,6 +832,7 @@ int swcu_synchronize(swcu_ctx *c, long *bad_cells)
     SWCU_CUDA(cudaMemsetAsync(c->bad_dev, 0, sizeof(int), c->st));
     SWCU_CUDA(cudaStreamSynchronize(c->st));
     SWCU_CUDA(cudaStreamSynchronize(c->comm_st));
+    SWCU_CUDA(cudaStreamSynchronize(c->bnd_st));
     const long bad = *c->bad_host;
     if (bad_cells) *bad_cells = bad;
     if (bad) { set_error("check_ssh_err: %ld sea cells with |ssh| >= 1e4 or NaN", bad); return SWCU_ERR_BLOWUP; }
