@@ -233,3 +233,49 @@ def test_striped_upload_equals_whole_upload(swlib, cuda_device):
     o.step(20); b.step(20)
     for f in STATE:
         assert np.array_equal(b.get(f), o.get(f)), f
+
+
+@pytest.mark.parametrize("shape", [(5, 5), (6, 9), (12, 7), (20, 6), (35, 12)])
+def test_tiny_basins(swlib, cuda_device, shape):
+    """Blocks smaller than one tile / one TMA box (down to a single computational cell)."""
+    nx, ny = shape
+    o = OracleModel(make_config(nx, ny, keep_mu=1), None)
+    o.step(12)
+    for mode in (MODE_REFERENCE, MODE_FUSED):
+        m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mode=mode, keep_mu=True)
+        m.step(12)
+        assert m.block.synchronize() == 0
+        for f in STATE:
+            assert np.array_equal(m.get(f), o.get(f)), (f, shape, mode)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_masks_and_depths(swlib, cuda_device, seed):
+    """Random sea/land masks (isolated cells, one-cell channels, diagonal contacts) with random
+    bathymetry: the coastline cases the mask logic has to get right (nsea = 1, 2, 3, 4 interpolation
+    weights, lcu/lcv vs llu/llv)."""
+    rng = np.random.default_rng(seed)
+    nx, ny = 61, 47
+    mask = (rng.random((ny, nx)) < 0.35).astype(np.int32)
+    mask[:2] = 1; mask[-2:] = 1; mask[:, :2] = 1; mask[:, -2:] = 1
+    mask[ny // 2 - 2:ny // 2 + 3, nx // 2 - 2:nx // 2 + 3] = 0
+    o = OracleModel(make_config(nx, ny, keep_mu=1, r_diss=5e-6), mask)
+    hrest = 50.0 + 100.0 * rng.random((ny, nx))
+    o.set("hhq_rest", hrest)
+    # redo the init-time hh_init with the new bathymetry (control/init_data.f90:60-63)
+    from oracle_lib import call_kernel
+    f4 = {n: o.get(n) for n in ("lu", "llu", "llv", "luh", "dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb")}
+    outs = {n: o.get(n) for n in ("hhq", "hhq_p", "hhq_n", "hhu", "hhu_p", "hhu_n", "hhv", "hhv_p", "hhv_n",
+                                  "hhh", "hhh_p", "hhh_n")}
+    call_kernel("hh_init_kernel", o.block_dims(0), 1, *[f4[n] for n in f4], *[outs[n] for n in outs],
+                o.get("ssh"), o.get("sshp"), o.get("hhq_rest"))
+    for n, arr in outs.items():
+        o.set(n, arr)
+    o.step(15)
+    for mode in (MODE_REFERENCE, MODE_FUSED):
+        m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=mode, keep_mu=True, r_diss=5e-6)
+        m.block.upload("hhq_rest", hrest)
+        m.block.hh_init()
+        m.step(15)
+        for f in STATE:
+            assert np.array_equal(m.get(f), o.get(f)), (f, seed, mode)
