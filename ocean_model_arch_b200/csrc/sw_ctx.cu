@@ -417,7 +417,7 @@ int step_fused(swcu_ctx *c, double tau)
     }
 
     const int ns = g.ny_start, ne = g.ny_end;
-    const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(a);
+    const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(g, a);
     StepMaps maps;
     if (tiled) {
         const double *src[8] = {a.ssh, a.sshp, a.u, a.up, a.v, a.vp, a.h_r, a.mu};

@@ -40,7 +40,7 @@ int launch_update(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t
 // the whole step for rows [n0..n1] in ONE launch (TMA-staged shared-memory tiles); needs a.tab
 int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, int variant,
                       cudaStream_t st);
-bool step_tiled_supported(const FusedArgs &a);
+bool step_tiled_supported(const Geo &g, const FusedArgs &a);
 void step_tile_box(int variant, int *box_w, int *box_h);
 // Builds the per-row tables from column nx_start of the nine real(4) arrays and counts (into
 // *nonrow_dev) the cells whose values differ from their row's entry.

@@ -125,7 +125,7 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
     const int tid = threadIdx.x;
     const int i0 = g.nx_start + blockIdx.x * TX, j0 = n0 + blockIdx.y * TY;
     const int ax = i0 - HALO - g.bx1, ay = j0 - HALO - g.by1;  // tile origin in array coordinates (>= 0)
-    const int w = g.bx2 - g.bx1 + 1, h = g.by2 - g.by1 + 1;
+    const int h = g.by2 - g.by1 + 1;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
@@ -142,13 +142,40 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
                          ::"r"(smem_u32(in + k * TILE)), "l"(reinterpret_cast<unsigned long long>(&maps.m[k])),
                          "r"(ax), "r"(ay), "r"(smem_u32(bar)) : "memory");
     }
-    for (int idx = tid; idx < TILE; idx += THREADS) {  // mask bytes: plain loads
-        const int lx = idx % IW, ly = idx / IW, gx = ax + lx, gy = ay + ly;
-        mk[idx] = (gx < w && gy < h) ? a.mask[(long)gy * g.pitch + gx] : (unsigned char)0;
-    }
-    for (int idx = tid; idx < T_COUNT * CFG::TROWS; idx += THREADS) {  // this tile's rows of the metric tables
-        const int t = idx / CFG::TROWS, rr = idx % CFG::TROWS;
-        stab[idx] = __ldg(a.tab + (long)t * a.tab_h + ay + rr);   // the table carries slack rows past h
+    // Mask bytes and this tile's rows of the metric tables: plain loads, ALL issued before any is
+    // consumed, so they cost one memory round trip that overlaps the TMA flight (a load-then-store
+    // loop cost three serialized round trips per CTA: 25 % of all stall samples in ncu).
+    {
+        constexpr int WORDS_PER_ROW = IW / 4;                  // 9 four-byte words per 36-byte mask row
+        constexpr int NW = WORDS_PER_ROW * IH;                 // rows start 4-byte aligned: ax % 32 == 0
+        constexpr int MW = (NW + THREADS - 1) / THREADS;
+        constexpr int NT = T_COUNT * CFG::TROWS;
+        constexpr int MT = (NT + THREADS - 1) / THREADS;
+        unsigned mw[MW];
+        double tv[MT];
+#pragma unroll
+        for (int k = 0; k < MW; ++k) {
+            const int idx = tid + k * THREADS, ly = idx / WORDS_PER_ROW, wx = idx % WORDS_PER_ROW;
+            const int gy = ay + ly, gx = ax + 4 * wx;
+            // columns past w but inside the pitch are zero padding; rows past h are outside the plane
+            mw[k] = (idx < NW && gy < h && gx + 3 < g.pitch)
+                        ? __ldg(reinterpret_cast<const unsigned *>(a.mask + (long)gy * g.pitch + gx)) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            const int idx = tid + k * THREADS, t = idx / CFG::TROWS, rr = idx % CFG::TROWS;
+            tv[k] = idx < NT ? __ldg(a.tab + (long)t * a.tab_h + ay + rr) : 0.0;  // the table carries slack rows past h
+        }
+#pragma unroll
+        for (int k = 0; k < MW; ++k) {
+            const int idx = tid + k * THREADS;
+            if (idx < NW) reinterpret_cast<unsigned *>(mk)[idx] = mw[k];
+        }
+#pragma unroll
+        for (int k = 0; k < MT; ++k) {
+            const int idx = tid + k * THREADS;
+            if (idx < NT) stab[idx] = tv[k];
+        }
     }
     {
         unsigned done = 0;
@@ -303,7 +330,11 @@ int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, in
     }
 }
 
-bool step_tiled_supported(const FusedArgs &a) { return a.trans && a.lat && a.tab != nullptr; }
+// (the mask tile is staged with 4-byte loads: tile rows must start 4-byte aligned in the mask plane)
+bool step_tiled_supported(const Geo &g, const FusedArgs &a)
+{
+    return a.trans && a.lat && a.tab != nullptr && (g.nx_start - HALO - g.bx1) % 4 == 0;
+}
 
 // TMA box (columns, rows) of a tile variant
 void step_tile_box(int variant, int *box_w, int *box_h)
