@@ -205,6 +205,13 @@ int swcu_download(swcu_ctx *ctx, int field, void *host);
  * n = bnd_y1 + first_row); host points at nrows x (bnd_x2-bnd_x1+1) contiguous values.  Lets a host
  * with less memory than the device stream a block in stripes. */
 int swcu_upload_rows(swcu_ctx *ctx, int field, const void *host, int first_row, int nrows);
+/* The record local_output writes for a field (control/output.f90:101-135, tools/io.f90:325-352):
+ * the block interior nx_start..nx_end x ny_start..ny_end, converted to real(4)
+ * (copy_from_real8, core/data_types.f90:438-452), with undef = -1.0e32 (shared/system.f90:10) where
+ * |lu| < 0.5, m fastest.  Built on the device; `host` receives (nx_end-nx_start+1)*(ny_end-ny_start+1)
+ * floats -- a quarter of the bytes of the full real(8) block the reference copies back first
+ * (model.f90:181).  real(8) fields only. */
+int swcu_output_record(swcu_ctx *ctx, int field, float *host);
 /* Same, but the other side is a DEVICE pointer in the reference layout (for callers that keep
  * their own device arrays, e.g. CUDA-Fortran field_device). */
 int swcu_upload_from_device(swcu_ctx *ctx, int field, const void *dev);

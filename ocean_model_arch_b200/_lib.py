@@ -78,6 +78,7 @@ _SIGNATURES = {
     "swcu_upload": [_P, _I, _P],
     "swcu_upload_rows": [_P, _I, _P, _I, _I],
     "swcu_download": [_P, _I, _P],
+    "swcu_output_record": [_P, _I, _P],
     "swcu_upload_from_device": [_P, _I, _P],
     "swcu_download_to_device": [_P, _I, _P],
     "swcu_set_option": [_P, C.c_char_p, _I],

@@ -478,13 +478,6 @@ int step_fused(swcu_ctx *c, double tau)
 }
 
 template <typename T>
-int copy_in(swcu_ctx *c, T *dst, const T *src, cudaMemcpyKind kind)
-{
-    SWCU_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->pitch * sizeof(T), src, (size_t)c->w * sizeof(T),
-                                (size_t)c->w * sizeof(T), (size_t)c->h, kind, c->st));
-    return SWCU_OK;
-}
-template <typename T>
 int copy_in_rows(swcu_ctx *c, T *dst, const T *src, int row0, int nrows, cudaMemcpyKind kind)
 {
     SWCU_CUDA(cudaMemcpy2DAsync(dst + (size_t)row0 * c->pitch, (size_t)c->pitch * sizeof(T), src, (size_t)c->w * sizeof(T),
@@ -749,6 +742,35 @@ int swcu_destroy(swcu_ctx *c)
 
 int swcu_upload(swcu_ctx *c, int field, const void *host) { return upload_impl(c, field, host, false); }
 int swcu_upload_from_device(swcu_ctx *c, int field, const void *dev) { return upload_impl(c, field, dev, true); }
+int swcu_output_record(swcu_ctx *c, int field, float *host)
+{
+    if (!c || !host) { set_error("null argument"); return SWCU_ERR_ARG; }
+    if (!is_f8(field)) { set_error("output records exist for real(8) fields only"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    const double *src = c->f8[field];
+    if (fused) {
+        if (field == SWCU_F_SSHN) src = c->f8[SWCU_F_SSH];
+        else if (field == SWCU_F_UBRTRN) src = c->f8[SWCU_F_UBRTR];
+        else if (field == SWCU_F_VBRTRN) src = c->f8[SWCU_F_VBRTR];
+        else if (field == SWCU_F_FF1N && c->p.use_tracers) src = c->f8[SWCU_F_FF1];
+        else if (!fused_keeps8(c, field) && !((field == SWCU_F_FF1 || field == SWCU_F_FF1P) && c->p.use_tracers)) src = nullptr;
+    }
+    if (!src) { set_error("field %d is not resident", field); return SWCU_ERR_STATE; }
+    const size_t n = (size_t)(c->d.nx_end - c->d.nx_start + 1) * (size_t)(c->d.ny_end - c->d.ny_start + 1);
+    float *tmp = nullptr;
+    SWCU_CUDA(cudaMalloc((void **)&tmp, n * sizeof(float)));
+    int rc = launch_output_record(c->g, src, fused ? c->mask : nullptr, fused ? nullptr : F4(c, SWCU_F_LU), tmp, c->st);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, c->st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "output record copy");
+    }
+    cudaStreamSynchronize(c->st);
+    cudaFree(tmp);
+    c->launches++;
+    return rc;
+}
+
 int swcu_upload_rows(swcu_ctx *c, int field, const void *host, int first_row, int nrows)
 {
     return upload_impl(c, field, host, false, first_row, nrows);

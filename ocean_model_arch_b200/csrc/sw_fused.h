@@ -48,6 +48,9 @@ int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, in
                         const float *const *arr_list_dev, cudaStream_t st);
 // expl_tracer for rows [n0..n1] in one launch; reads a.ssh_o .. a.v_o (the state the step just wrote)
 int launch_tracer(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);
+// fp32 output record of the interior with undef on land (either a mask byte plane or a real(4) lu)
+int launch_output_record(const Geo &g, const double *field, const unsigned char *mask_bits, const float *lu,
+                         float *out, cudaStream_t st);
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 

@@ -397,6 +397,29 @@ int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, in
     return launched("build_tables");
 }
 
+// ---- output record (control/output.f90:101-135, tools/io.f90:343-348) --------------------------
+namespace {
+__global__ void k_output_record(Geo g, const double *__restrict__ f, const unsigned char *__restrict__ bits,
+                                const float *__restrict__ lu, float *__restrict__ out)
+{
+    const int m = g.nx_start + blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = g.ny_start + blockIdx.y;
+    if (m > g.nx_end) return;
+    const long c = ix(g, m, n);
+    const bool sea = bits ? (bits[c] & MB_LU) != 0 : !(fabsf(lu[c]) < 0.5f);
+    const long o = (long)(n - g.ny_start) * (g.nx_end - g.nx_start + 1) + (m - g.nx_start);
+    out[o] = sea ? (float)f[c] : -1.0e32f;   // real(x, wp4) rounds to nearest, like cvt.rn.f32.f64
+}
+}  // namespace
+
+int launch_output_record(const Geo &g, const double *field, const unsigned char *mask_bits, const float *lu,
+                         float *out, cudaStream_t st)
+{
+    const dim3 grid((unsigned)((g.nx_end - g.nx_start + 256) / 256), (unsigned)(g.ny_end - g.ny_start + 1), 1);
+    k_output_record<<<grid, 256, 0, st>>>(g, field, mask_bits, lu, out);
+    return launched("output_record");
+}
+
 // ---- mask packing -----------------------------------------------------------------------------
 namespace {
 __global__ void k_mask_set(long total, const float *__restrict__ src, unsigned char *__restrict__ bits, int bit)

@@ -216,6 +216,13 @@ class DeviceBlock:
         check(self.L.swcu_download(self.h, FIELD_ID[name], _ptr(out)))
         return out
 
+    def output_record(self, name):
+        """fp32 interior record with undef on land, as local_output writes it (control/output.f90:101-135)."""
+        d = self.dims
+        out = np.empty((d.ny_end - d.ny_start + 1, d.nx_end - d.nx_start + 1), dtype=np.float32)
+        check(self.L.swcu_output_record(self.h, FIELD_ID[name], _ptr(out)))
+        return out
+
     def download_ptr(self, name, host_ptr):
         check(self.L.swcu_download(self.h, FIELD_ID[name], C.c_void_p(host_ptr)))
 

@@ -279,3 +279,20 @@ def test_random_masks_and_depths(swlib, cuda_device, seed):
         m.step(15)
         for f in STATE:
             assert np.array_equal(m.get(f), o.get(f)), (f, seed, mode)
+
+
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_FUSED])
+def test_output_record(swlib, cuda_device, mode):
+    """RESULTS/ssh.dat record: real(4) interior with undef = -1e32 on land (control/output.f90:101-135,
+    tools/io.f90:343-348), built on the device."""
+    nx, ny = 75, 58
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=mode)
+    o.step(20); m.step(20)
+    want = o.get("ssh").astype(np.float32)
+    want[np.abs(o.get("lu")) < 0.5] = np.float32(-1.0e32)
+    got = m.block.output_record("ssh")
+    assert got.dtype == np.float32 and got.shape == (ny - 4, nx - 4)
+    assert np.array_equal(got, want[2:-2, 2:-2])
+    assert (got == np.float32(-1.0e32)).sum() == int((mask[2:-2, 2:-2] == 1).sum())
