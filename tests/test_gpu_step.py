@@ -296,3 +296,26 @@ def test_output_record(swlib, cuda_device, mode):
     assert got.dtype == np.float32 and got.shape == (ny - 4, nx - 4)
     assert np.array_equal(got, want[2:-2, 2:-2])
     assert (got == np.float32(-1.0e32)).sum() == int((mask[2:-2, 2:-2] == 1).sum())
+
+
+def test_config1_shipped_basin_604_and_1000_steps(swlib, cuda_device):
+    """BASELINE config 1, the parity anchor: the shipped basin.par / sw.par / ocean_run.par
+    (1525 x 1115, mask none, flat 100 m, spherical, tau = 1 s, 604 steps) and its 1000-step extension.
+    The oracle runs it as 1 x 16 blocks (bitwise decomposition-invariant, tests/test_oracle.py) to
+    finish in seconds; bar: relative L2 <= 1e-12 (north star) -- and in fact bitwise."""
+    run = model.RunPar()
+    assert run.num_step_max == 604
+    bp = model.BasinPar()
+    o = OracleModel(make_config(bp.nx, bp.ny, bnx=1, bny=16, nthreads=16), None)
+    m = model.ShallowWaterModel(bp, model.SwPar(), run, mode=MODE_FUSED)
+    done = 0
+    for steps in (604, 1000):
+        assert o.step(steps - done) == 0
+        m.step(steps - done)
+        done = steps
+        assert m.block.synchronize() == 0
+        for f in ("ssh", "ubrtr", "vbrtr"):
+            a, b = m.get(f), o.get(f)
+            rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+            assert rel <= 1e-12, (f, steps, rel)
+            assert np.array_equal(a, b), (f, steps)
