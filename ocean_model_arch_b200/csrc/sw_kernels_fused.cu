@@ -291,12 +291,15 @@ namespace {
 template <class CFG, bool T, bool L, bool R, bool D>
 int step_launch(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in for > 48 KB of dynamic shared memory is per device: remember which devices have it
+    static unsigned long long attr_set = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set >> (dev & 63) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k_step<CFG, T, L, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)CFG::SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_step)");
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     const dim3 grid((unsigned)((g.nx_end - g.nx_start + TX) / TX), (unsigned)((n1 - n0 + CFG::TY) / CFG::TY), 1);
     k_step<CFG, T, L, R, D><<<grid, CFG::THREADS, CFG::SMEM, st>>>(maps, g, a, n0, n1);

@@ -34,6 +34,32 @@ def main():
     mask = basins.island_mask(nx, ny)
     bp = model.BasinPar(nx=nx, ny=ny)
     ok = True
+    # the reference's sync_test (shared/mpp/syncborder_block2D_gen_test.fi:10-97): interiors hold i*j, after
+    # the halo exchange every halo row a neighbour owns must hold i*j too
+    for mode, nrows in ((MODE_FUSED, 2), (MODE_REFERENCE, 1)):
+        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world)
+        ids = [model.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        m.attach_comm(ids[0])
+        d = m.dims
+        jj, ii = np.mgrid[d.bnd_y1:d.bnd_y2 + 1, d.bnd_x1:d.bnd_x2 + 1]
+        pat = (ii * jj).astype(np.float64)
+        mine = np.zeros_like(pat)
+        r0, r1 = d.ny_start - d.bnd_y1, d.ny_end - d.bnd_y1
+        mine[r0:r1 + 1] = pat[r0:r1 + 1]
+        m.block.upload("mu", mine)
+        m.block.halo_exchange("mu")
+        got = m.block.download("mu")
+        lo = r0 - nrows if rank > 0 else r0
+        hi = r1 + nrows if rank < world - 1 else r1
+        good = np.array_equal(got[lo:hi + 1], pat[lo:hi + 1]) and not got[:lo].any() and not got[hi + 1:].any()
+        flag = torch.tensor([1 if good else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok &= bool(flag.item())
+        if rank == 0:
+            print(f"sync_test mode={mode} halo={nrows}: {'ok' if flag.item() else 'FAILED'}", flush=True)
+        m.block.close()
+        dist.barrier()
     for mode, tiled in ((MODE_FUSED, 1), (MODE_FUSED, 0), (MODE_REFERENCE, 0)):
         m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True)
         if mode == MODE_FUSED:

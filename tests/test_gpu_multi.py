@@ -23,3 +23,4 @@ def test_slabs_over_nccl_bitwise(swlib, cuda_device, shape):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("bitwise equal") == 3, r.stdout
+    assert r.stdout.count("sync_test") == 2 and "FAILED" not in r.stdout, r.stdout
