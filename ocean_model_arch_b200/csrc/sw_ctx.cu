@@ -142,6 +142,10 @@ struct swcu_ctx {
     double *tab = nullptr;
     const float **arr_list_dev = nullptr;
     int *nonrow_dev = nullptr;
+    bool masks_dirty = true, want_land_skip = true;  // all-land tile flags, rebuilt after a mask upload
+    unsigned char *tile_land = nullptr;
+    size_t tile_land_cap = 0;
+    int tile_land_n0 = 0, tile_land_n1 = -1;  // row range of the launch the flags describe
     bool want_tiled = true;                   // one-launch TMA-tiled step when the tables are usable
     int tile_variant = 4;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
@@ -330,6 +334,7 @@ void fill_static_args(swcu_ctx *c, FusedArgs &a)
     a.dxh = F4(c, SWCU_F_DXH); a.dyh = F4(c, SWCU_F_DYH); a.dxb = F4(c, SWCU_F_DXB); a.dyb = F4(c, SWCU_F_DYB);
     a.rlh_s = F4(c, SWCU_F_RLH_S); a.rdis = c->has_rdiss ? F4(c, SWCU_F_R_DISS) : nullptr;
     a.mask = c->mask; a.bad = c->bad_dev;
+    a.tile_land = nullptr;
 }
 
 // (re)builds the per-row metric tables and decides whether they may replace the 2-D arrays
@@ -418,6 +423,26 @@ int step_fused(swcu_ctx *c, double tau)
 
     const int ns = g.ny_start, ne = g.ny_end;
     const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(g, a);
+    // rows of the main launch: everything, or the interior between the two boundary strips
+    int main0 = ns, main1 = ne;
+    if (c->comm) {
+        if (c->rank > 0) main0 = (ns + 1 < ne ? ns + 1 : ne) + 1;
+        if (c->rank + 1 < c->nranks && main0 <= ne) main1 = (ne - 1 > main0 ? ne - 1 : main0) - 1;
+    }
+    if (tiled && (c->masks_dirty || c->tile_land_n0 != main0 || c->tile_land_n1 != main1)) {
+        // (re)build the all-land tile flags of the main launch
+        int ntx = 0, nty = 0;
+        step_tile_grid(g, c->tile_variant, main0, main1, &ntx, &nty);
+        const size_t need = (size_t)ntx * nty;
+        if (need > c->tile_land_cap) {
+            if (c->tile_land) { cudaFree(c->tile_land); c->bytes -= (long)c->tile_land_cap; }
+            c->tile_land = nullptr; c->tile_land_cap = 0;
+            RC(dev_alloc(c, (void **)&c->tile_land, need ? need : 1));
+            c->tile_land_cap = need ? need : 1;
+        }
+        RC(launch_tile_land(g, c->mask, c->tile_variant, main0, main1, c->tile_land, c->st));
+        c->masks_dirty = false; c->tile_land_n0 = main0; c->tile_land_n1 = main1;
+    }
     StepMaps maps;
     if (tiled) {
         const double *src[8] = {a.ssh, a.sshp, a.u, a.up, a.v, a.vp, a.h_r, a.mu};
@@ -429,6 +454,8 @@ int step_fused(swcu_ctx *c, double tau)
     // rows [r0..r1] of the n+1 state: one tiled launch, or the update stage of the two-launch path
     auto rows = [&](int r0, int r1, cudaStream_t st) -> int {
         if (r1 < r0) return SWCU_OK;
+        // the flags describe the tile grid of the main launch only; the boundary strips do not use them
+        a.tile_land = (tiled && c->want_land_skip && r0 == main0 && r1 == main1) ? c->tile_land : nullptr;
         RC(prof_mark(c, 1, true, st));
         RC(tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, st) : launch_update(g, a, r0, r1, st));
         RC(prof_mark(c, 1, false, st));
@@ -589,6 +616,7 @@ int upload_impl(swcu_ctx *c, int field, const void *src, bool from_device, int r
                 if (e != cudaSuccess) rc = cuda_fail(e, "mask upload");
             }
             if (!rc) rc = launch_mask_set((long)cnt, tmp, c->mask + (size_t)row0 * c->pitch, bit, c->st);
+            c->masks_dirty = true;
             cudaStreamSynchronize(c->st);
             cudaFree(tmp);
             return rc;
@@ -726,7 +754,7 @@ int swcu_destroy(swcu_ctx *c)
     for (auto &p : c->alt) cudaFree(p);
     for (auto &p : c->alt_ff) cudaFree(p);
     cudaFree(c->mask); cudaFree(c->bad_dev);
-    cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev);
+    cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev); cudaFree(c->tile_land);
     if (c->bad_host) cudaFreeHost(c->bad_host);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
@@ -783,7 +811,8 @@ int swcu_set_option(swcu_ctx *c, const char *name, int value)
     if (!c || !name) { set_error("null argument"); return SWCU_ERR_ARG; }
     if (!strcmp(name, "metric_tables")) { c->want_tables = value != 0; c->metrics_dirty = true; return SWCU_OK; }
     if (!strcmp(name, "tiled")) { c->want_tiled = value != 0; return SWCU_OK; }
-    if (!strcmp(name, "tile_variant")) { c->tile_variant = value; c->tmaps.clear(); return SWCU_OK; }
+    if (!strcmp(name, "tile_variant")) { c->tile_variant = value; c->tmaps.clear(); c->masks_dirty = true; return SWCU_OK; }
+    if (!strcmp(name, "land_skip")) { c->want_land_skip = value != 0; return SWCU_OK; }
     set_error("unknown option %s", name);
     return SWCU_ERR_ARG;
 }

@@ -25,6 +25,11 @@ struct FusedArgs {
     const double *tab;  // per-row metric tables [T_COUNT][tab_h], nullptr <=> use the 2-D real(4) arrays
     int tab_h;
     const unsigned char *mask;
+    // one byte per tile of the main (interior / full-range) tiled launch: 1 <=> every output cell of the tile is land, so
+    // the tile is skipped (land cells never change; both ping-pong buffers already hold them).
+    // nullptr for strip launches / other paths.  The B200 analogue of the reference's land-block
+    // skipping (core/decomposition.f90:508-512 counts all-land blocks).
+    const unsigned char *tile_land;
     int *bad;  // K11 counter
     Tau tau;
     double ts, ffs;
@@ -42,6 +47,10 @@ int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, in
                       cudaStream_t st);
 bool step_tiled_supported(const Geo &g, const FusedArgs &a);
 void step_tile_box(int variant, int *box_w, int *box_h);
+// tile grid (columns, rows of tiles) of the full-range launch, and the all-land flags for it
+void step_tile_grid(const Geo &g, int variant, int n0, int n1, int *ntx, int *nty);
+int launch_tile_land(const Geo &g, const unsigned char *mask, int variant, int n0, int n1, unsigned char *tile_land,
+                     cudaStream_t st);
 // Builds the per-row tables from column nx_start of the nine real(4) arrays and counts (into
 // *nonrow_dev) the cells whose values differ from their row's entry.
 int launch_build_tables(const Geo &g, const FusedArgs &a, double *tab, int h, int *nonrow_dev,

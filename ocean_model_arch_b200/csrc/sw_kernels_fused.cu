@@ -122,6 +122,8 @@ k_step(const __grid_constant__ StepMaps maps, Geo g, FusedArgs a, int n0, int n1
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(mk + CFG::MASK_BYTES);
     double *stab = reinterpret_cast<double *>(mk + CFG::MASK_BYTES + 16);  // [T_COUNT][TROWS]
 
+    if (a.tile_land && a.tile_land[blockIdx.y * gridDim.x + blockIdx.x]) return;  // all-land tile (CTA-uniform)
+
     const int tid = threadIdx.x;
     const int i0 = g.nx_start + blockIdx.x * TX, j0 = n0 + blockIdx.y * TY;
     const int ax = i0 - HALO - g.bx1, ay = j0 - HALO - g.by1;  // tile origin in array coordinates (>= 0)
@@ -337,6 +339,45 @@ int launch_step_tiled(const StepMaps &maps, const Geo &g, const FusedArgs &a, in
 bool step_tiled_supported(const Geo &g, const FusedArgs &a)
 {
     return a.trans && a.lat && a.tab != nullptr && (g.nx_start - HALO - g.bx1) % 4 == 0;
+}
+
+namespace {
+int variant_ty(int variant) { return (variant == 3 || variant == 4 || variant < 1 || variant > 5) ? 8 : 16; }
+
+// one warp per tile: OR of the lu bits of the tile's output cells
+__global__ void k_tile_land(Geo g, const unsigned char *__restrict__ mask, int ty, int ntx, int nty, int n0, int n1,
+                            unsigned char *__restrict__ tile_land)
+{
+    const int t = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (t >= ntx * nty) return;
+    const int bx = t % ntx, by = t / ntx;
+    const int m = g.nx_start + bx * TX + lane;
+    int any = 0;
+    for (int k = 0; k < ty; ++k) {
+        const int n = n0 + by * ty + k;
+        if (m <= g.nx_end && n <= n1) any |= mask[ix(g, m, n)] & MB_LU;
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) tile_land[t] = any ? 0 : 1;
+}
+}  // namespace
+
+void step_tile_grid(const Geo &g, int variant, int n0, int n1, int *ntx, int *nty)
+{
+    const int ty = variant_ty(variant);
+    *ntx = (g.nx_end - g.nx_start + TX) / TX;
+    *nty = n1 >= n0 ? (n1 - n0 + ty) / ty : 0;
+}
+
+int launch_tile_land(const Geo &g, const unsigned char *mask, int variant, int n0, int n1, unsigned char *tile_land,
+                     cudaStream_t st)
+{
+    int ntx = 0, nty = 0;
+    step_tile_grid(g, variant, n0, n1, &ntx, &nty);
+    const int tiles = ntx * nty;
+    if (tiles == 0) return SWCU_OK;
+    k_tile_land<<<(unsigned)((tiles + 7) / 8), 256, 0, st>>>(g, mask, variant_ty(variant), ntx, nty, n0, n1, tile_land);
+    return launched("tile_land");
 }
 
 // TMA box (columns, rows) of a tile variant

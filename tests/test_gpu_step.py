@@ -319,3 +319,29 @@ def test_config1_shipped_basin_604_and_1000_steps(swlib, cuda_device):
             rel = np.linalg.norm(a - b) / np.linalg.norm(b)
             assert rel <= 1e-12, (f, steps, rel)
             assert np.array_equal(a, b), (f, steps)
+
+
+def test_all_land_tiles_are_skipped_safely(swlib, cuda_device):
+    """Tiles whose 32x8 output cells are all land exit before any load (the B200 analogue of the
+    reference's land-block skipping).  Results must not depend on it, uploads after the first step
+    (which change land cells in one ping-pong buffer only) must still propagate, and a later mask
+    upload must rebuild the flags."""
+    nx, ny = 230, 170
+    mask = basins.island_mask(nx, ny, ndisc=5)
+    assert (mask[2:-2, 2:-2].reshape(-1) == 1).mean() > 0.1      # the coast alone fills whole 32x8 tiles
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    a = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    b = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED, keep_mu=True)
+    b.block.set_option("land_skip", 0)
+    o.step(40); a.step(40); b.step(40)
+    for f in STATE:
+        assert np.array_equal(a.get(f), o.get(f)), f
+        assert np.array_equal(b.get(f), o.get(f)), f
+    # a host upload that writes garbage on land into ssh: the reference keeps it there unchanged forever
+    ssh = o.get("ssh").copy()
+    ssh[mask == 1] = 7.0
+    o.set("ssh", ssh); a.block.upload("ssh", ssh)
+    o.step(3); a.step(3)
+    for f in STATE:
+        assert np.array_equal(a.get(f), o.get(f)), f
+    assert (a.get("ssh")[mask == 1] == 7.0).all()
