@@ -32,7 +32,7 @@ int check_dims(const swcu_dims *d);
 // ---- launchers of the 1:1 kernels (sw_kernels_ref.cu).  All return SWCU_OK / SWCU_ERR_CUDA. ----
 int launch_sw_update_ssh(const Geo &g, double tau, const float *lu, const float *dx, const float *dy,
         const float *dxh, const float *dyh, const double *hhu, const double *hhv, double *sshn,
-        const double *sshp, const double *u, const double *v, cudaStream_t st);
+        const double *sshp, const double *u, const double *v, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_sw_update_uv(const Geo &g, double tau, const float *lcu, const float *lcv,
         const float *dxt, const float *dyt, const float *dxh, const float *dyh, const float *dxb, const float *dyb,
         const double *hhu, const double *hhun, const double *hhup,
@@ -40,34 +40,34 @@ int launch_sw_update_uv(const Geo &g, double tau, const float *lcu, const float 
         const double *u, double *un, const double *up, const double *v, double *vn, const double *vp,
         const float *rdis, const float *rlh_s, const double *RHSx, const double *RHSy,
         const double *RHSx_adv, const double *RHSy_adv, const double *RHSx_dif, const double *RHSy_dif,
-        cudaStream_t st);
+        cudaStream_t st, const MetRow *mr = nullptr, const Tau *tau_exact = nullptr);
 int launch_sw_next_step(const Geo &g, double ts, const float *lu, const float *lcu, const float *lcv,
         double *ssh, double *sshn, double *sshp, double *u, double *un, double *up,
         double *v, double *vn, double *vp, cudaStream_t st);
 int launch_uv_trans_vort(const Geo &g, const float *luu, const float *dxt, const float *dyt,
-        const float *dxb, const float *dyb, const double *u, const double *v, double *vort, cudaStream_t st);
+        const float *dxb, const float *dyb, const double *u, const double *v, double *vort, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_uv_trans(const Geo &g, const float *lcu, const float *lcv, const float *luu,
         const float *dxh, const float *dyh, const double *u, const double *v, const double *vort,
-        const double *hu, const double *hv, const double *hh, double *RHSx, double *RHSy, cudaStream_t st);
+        const double *hu, const double *hv, const double *hh, double *RHSx, double *RHSy, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_uv_diff2(const Geo &g, const float *lcu, const float *lcv,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
         const double *mu, const double *str_t, const double *str_s, const double *hq, const double *hh,
-        double *RHSx, double *RHSy, cudaStream_t st);
+        double *RHSx, double *RHSy, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_stress_components(const Geo &g, const float *lu, const float *luu,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
-        const double *u, const double *v, double *str_t, double *str_s, cudaStream_t st);
+        const double *u, const double *v, double *str_t, double *str_s, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_hh_init(const Geo &g, int ffs, const float *lu, const float *llu, const float *llv, const float *luh,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
         double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
         double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn,
-        const double *sh, const double *shp, const double *h_r, cudaStream_t st);
+        const double *sh, const double *shp, const double *h_r, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_hh_update(const Geo &g, const float *lu, const float *llu, const float *llv, const float *luh,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
-        double *hqn, double *hun, double *hvn, double *hhn, const double *sh, const double *h_r, cudaStream_t st);
+        double *hqn, double *hun, double *hvn, double *hhn, const double *sh, const double *h_r, cudaStream_t st, const MetRow *mr = nullptr);
 int launch_hh_shift(const Geo &g, double ts, const float *lu, const float *llu, const float *llv, const float *luh,
         double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
         double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn, cudaStream_t st);

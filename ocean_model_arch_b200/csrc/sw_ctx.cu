@@ -249,6 +249,8 @@ int prof_mark(swcu_ctx *c, int kind, bool begin, cudaStream_t st = nullptr)
 }
 #define PROF(kind, call) do { RC(prof_mark(c, kind, true)); RC(call); RC(prof_mark(c, kind, false)); } while (0)
 
+int prepare_metrics(swcu_ctx *c);
+
 // control/shallow_water/shallow_water.f90:22-94 with the binders' argument choice
 // (interface/shallow_water/sw_interface.f90), then control/tracer.f90:44-61
 int step_reference(swcu_ctx *c, double tau)
@@ -261,31 +263,42 @@ int step_reference(swcu_ctx *c, double tau)
           *lcv = F4(c, SWCU_F_LCV), *llu = F4(c, SWCU_F_LLU), *llv = F4(c, SWCU_F_LLV);
     float *dx = F4(c, SWCU_F_DX), *dy = F4(c, SWCU_F_DY), *dxt = F4(c, SWCU_F_DXT), *dyt = F4(c, SWCU_F_DYT),
           *dxh = F4(c, SWCU_F_DXH), *dyh = F4(c, SWCU_F_DYH), *dxb = F4(c, SWCU_F_DXB), *dyb = F4(c, SWCU_F_DYB);
+    // With row-constant metrics the 1:1 kernels read the context's per-row tables (no conversions, exact
+    // mdiv divisions); otherwise the real(4) arrays, exactly as Level A does.  Same bits either way.
+    if (c->metrics_dirty) RC(prepare_metrics(c));
+    const MetRow mrow{c->tab, c->h, 0};
+    const MetRow *mr = c->use_tables ? &mrow : nullptr;
+    Tau tt;
+    {
+        int ex = 0;
+        const double mant = frexp(tau, &ex);
+        tt.tau = tau; tt.rtau = 1.0 / tau; tt.pow2 = (mant == 0.5 && tau > 1e-300 && tau < 1e300) ? 1 : 0; tt.exact = 1;
+    }
 
     RC(launch_sw_update_ssh(g, tau, lu, dx, dy, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_SSHN],
-                            F[SWCU_F_SSHP], F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], st));
+                            F[SWCU_F_SSHP], F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], st, mr));
     c->launches++;
     RC(sync_fields(c, {SWCU_F_SSHN}));
     if (p.full_free_surface > 0) {
         RC(launch_hh_update(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHQ_N],
-                            F[SWCU_F_HHU_N], F[SWCU_F_HHV_N], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_HHQ_REST], st));
+                            F[SWCU_F_HHU_N], F[SWCU_F_HHV_N], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_HHQ_REST], st, mr));
         c->launches++;
         RC(sync_fields(c, {SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N}));
     }
     if (p.trans_terms > 0) {
-        RC(launch_uv_trans_vort(g, luu, dxt, dyt, dxb, dyb, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT], st));
+        RC(launch_uv_trans_vort(g, luu, dxt, dyt, dxb, dyb, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT], st, mr));
         RC(sync_fields(c, {SWCU_F_VORT}));
         RC(launch_uv_trans(g, lcu, lcv, luu, dxh, dyh, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT],
-                           F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_HHH], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV], st));
+                           F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_HHH], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV], st, mr));
         c->launches += 2;
         RC(sync_fields(c, {SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P}));
     }
     if (p.ksw_lat > 0) {
         RC(launch_stress_components(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_UBRTRP],
-                                    F[SWCU_F_VBRTRP], F[SWCU_F_STR_T], F[SWCU_F_STR_S], st));
+                                    F[SWCU_F_VBRTRP], F[SWCU_F_STR_T], F[SWCU_F_STR_S], st, mr));
         RC(sync_fields(c, {SWCU_F_STR_T, SWCU_F_STR_S}));
         RC(launch_uv_diff2(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_MU], F[SWCU_F_STR_T],
-                           F[SWCU_F_STR_S], F[SWCU_F_HHQ], F[SWCU_F_HHH], F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st));
+                           F[SWCU_F_STR_S], F[SWCU_F_HHQ], F[SWCU_F_HHH], F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr));
         c->launches += 2;
     }
     RC(launch_sw_update_uv(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHU], F[SWCU_F_HHU_N],
@@ -293,7 +306,7 @@ int step_reference(swcu_ctx *c, double tau)
                            F[SWCU_F_SSH], F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR],
                            F[SWCU_F_VBRTRN], F[SWCU_F_VBRTRP], F4(c, SWCU_F_R_DISS), F4(c, SWCU_F_RLH_S),
                            F[SWCU_F_RHSX], F[SWCU_F_RHSY], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV],
-                           F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st));
+                           F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr, &tt));
     c->launches++;
     RC(sync_fields(c, {SWCU_F_VBRTRN, SWCU_F_UBRTRN}));
     RC(launch_sw_next_step(g, p.time_smooth, lu, lcu, lcv, F[SWCU_F_SSH], F[SWCU_F_SSHN], F[SWCU_F_SSHP],
@@ -307,7 +320,7 @@ int step_reference(swcu_ctx *c, double tau)
         RC(launch_hh_init(g, p.full_free_surface, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
                           F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
                           F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
-                          F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], st));
+                          F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], st, mr));
         c->launches += 2;
         RC(sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH}));
     }

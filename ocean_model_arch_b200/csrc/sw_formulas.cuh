@@ -171,6 +171,22 @@ __device__ __forceinline__ double f_interp4_b(double hq_c, double hq_e, double h
                              + hq_n * dx_n * dy_n * lu_n + hq_en * dx_en * dy_en * lu_en, nsea), dxb, rdxb), dyb, rdyb);
 }
 
+// x / slu for an arbitrary real(4)-sum slu: 1, 2 and 4 are exact scalings (same bits as the division),
+// everything else divides
+__device__ __forceinline__ double div_slu_any(double x, double slu)
+{
+    if (slu == 1.0) return x;
+    if (slu == 2.0) return x * 0.5;
+    if (slu == 4.0) return x * 0.25;
+    return x / slu;
+}
+// numerator of depth.f90:60-61
+__device__ __forceinline__ double hq_sum2(double hq_c, double hq_e, double dx_c, double dy_c, double lu_c,
+                                          double dx_e, double dy_e, double lu_e)
+{
+    return hq_c * dx_c * dy_c * lu_c + hq_e * dx_e * dy_e * lu_e;
+}
+
 // kernel/shallow_water/depth.f90:81-85
 __device__ __forceinline__ double f_interp4(double hq_c, double hq_e, double hq_n, double hq_en,
         double dx_c, double dy_c, double lu_c, double dx_e, double dy_e, double lu_e,

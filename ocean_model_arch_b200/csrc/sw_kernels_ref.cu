@@ -22,6 +22,21 @@ inline int launched(const char *what)
     return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
 }
 
+// Level B (REFERENCE mode) may hand the kernels the context's per-row metric tables: ROW = true reads
+// them (no real(4)->real(8) conversions, exact mdiv divisions), ROW = false reads the real(4) arrays
+// the reference passes (Level A, any grid).
+template <bool ROW> struct Pick {
+    static __device__ __forceinline__ const MetGen &get(const MetGen &a, const MetRow &) { return a; }
+};
+template <> struct Pick<true> {
+    static __device__ __forceinline__ const MetRow &get(const MetGen &, const MetRow &b) { return b; }
+};
+#define SWCU_LAUNCH_ROW(kern, grid, ...)                                          \
+    do {                                                                          \
+        if (mr) kern<true><<<grid, kBlock, 0, st>>>(g, *mr, __VA_ARGS__);         \
+        else kern<false><<<grid, kBlock, 0, st>>>(g, MetRow{nullptr, 0, 0}, __VA_ARGS__); \
+    } while (0)
+
 #define SWCU_CELL(m0, n0, m1, n1)                          \
     const int m = (m0) + blockIdx.x * BX + threadIdx.x;    \
     const int n = (n0) + blockIdx.y * BY + threadIdx.y;    \
@@ -32,7 +47,8 @@ inline int launched(const char *what)
     (void)p; (void)r
 
 // K1 -- kernel/shallow_water/vel_ssh.f90:94-104
-__global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, double tau,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, MetRow mr, double tau,
         const float *__restrict__ lu, const float *__restrict__ dx, const float *__restrict__ dy,
         const float *__restrict__ dxh, const float *__restrict__ dyh,
         const double *__restrict__ hhu, const double *__restrict__ hhv, double *__restrict__ sshn,
@@ -40,11 +56,13 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, double tau,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
-    if (on(lu[c])) sshn[c] = f_sshn(c, r, p, tau, mg, hhu, hhv, sshp, u, v);
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    if (on(lu[c])) sshn[c] = f_sshn(c, r, p, tau, mt, hhu, hhv, sshp, u, v);
 }
 
 // K7 -- kernel/shallow_water/vel_ssh.f90:163-193
-__global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, double tau,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, MetRow mr, Tau tt,
         const float *__restrict__ lcu, const float *__restrict__ lcv,
         const float *__restrict__ dxt, const float *__restrict__ dyt,
         const float *__restrict__ dxh, const float *__restrict__ dyh,
@@ -61,12 +79,12 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, double tau,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, dxt, dyt, dxh, dyh, dxb, dyb, rlh_s};
-    const Tau tt{tau, 0.0, 0, 0};  // Level A always divides
+    const auto &mt = Pick<ROW>::get(mg, mr);
     if (on(lcu[c]))
-        un[c] = f_un(c, r, p, tt, mg, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
+        un[c] = f_un(c, r, p, tt, mt, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
                      (double)(rdis[c] + rdis[c + 1]), hhh, ssh, v, up);
     if (on(lcv[c]))
-        vn[c] = f_vn(c, r, p, tt, mg, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
+        vn[c] = f_vn(c, r, p, tt, mt, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
                      (double)(rdis[c] + rdis[c + p]), hhh, ssh, u, vp);
 }
 
@@ -93,18 +111,21 @@ __global__ void __launch_bounds__(BX *BY) k_sw_next_step(Geo g, double ts,
 }
 
 // K3 -- kernel/shallow_water/vel_ssh.f90:269-279
-__global__ void __launch_bounds__(BX *BY) k_uv_trans_vort(Geo g, const float *__restrict__ luu,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_uv_trans_vort(Geo g, MetRow mr, const float *__restrict__ luu,
         const float *__restrict__ dxt, const float *__restrict__ dyt,
         const float *__restrict__ dxb, const float *__restrict__ dyb,
         const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ vort)
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, dxt, dyt, nullptr, nullptr, dxb, dyb, nullptr};
-    if (on(luu[c])) vort[c] = f_vort(c, r, p, mg, u, v);
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    if (on(luu[c])) vort[c] = f_vort(c, r, p, mt, u, v);
 }
 
 // K4 -- kernel/shallow_water/vel_ssh.f90:318-371
-__global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g, MetRow mr,
         const float *__restrict__ lcu, const float *__restrict__ lcv, const float *__restrict__ luu,
         const float *__restrict__ dxh, const float *__restrict__ dyh,
         const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ vort,
@@ -113,12 +134,14 @@ __global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
-    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, r, p, mg, (double)luu[c], (double)luu[c - p], u, v, vort, hu, hv, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, r, p, mg, u, v, vort, hu, hv, hh);
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, r, p, mt, (double)luu[c], (double)luu[c - p], u, v, vort, hu, hv, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh);
 }
 
 // K6 -- kernel/shallow_water/vel_ssh.f90:414-450
-__global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g, MetRow mr,
         const float *__restrict__ lcu, const float *__restrict__ lcv,
         const float *__restrict__ dx, const float *__restrict__ dy,
         const float *__restrict__ dxt, const float *__restrict__ dyt,
@@ -130,12 +153,14 @@ __global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
-    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, r, p, mg, hq[c], hq[c + 1], mu, str_t, str_s, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, r, p, mg, hq[c], hq[c + p], mu, str_t, str_s, hh);
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, r, p, mt, hq[c], hq[c + 1], mu, str_t, str_s, hh);
+    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, r, p, mt, hq[c], hq[c + p], mu, str_t, str_s, hh);
 }
 
 // K5 -- kernel/shallow_water/mixing.f90:38-56
-__global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g, MetRow mr,
         const float *__restrict__ lu, const float *__restrict__ luu,
         const float *__restrict__ dx, const float *__restrict__ dy,
         const float *__restrict__ dxt, const float *__restrict__ dyt,
@@ -146,29 +171,39 @@ __global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g,
 {
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
-    if (on(lu[c])) str_t[c] = f_str_t(c, r, p, mg, u, v);
-    if (on(luu[c])) str_s[c] = f_str_s(c, r, p, mg, u, v);
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    if (on(lu[c])) str_t[c] = f_str_t(c, r, p, mt, u, v);
+    if (on(luu[c])) str_s[c] = f_str_s(c, r, p, mt, u, v);
 }
 
 // the three interpolations of hh_init / hh_update for one source depth (depth.f90:57-94);
 // the T-point depth of the neighbours is re-evaluated in registers (same expression as the
 // whole-array statement) so the kernel needs no grid-wide ordering.
 struct Interp3 { double hu, hv, hh; };
-__device__ __forceinline__ Interp3 interp3(double q_c, double q_e, double q_n, double q_en, long c, int p,
-        const float *__restrict__ lu, const float *__restrict__ dx, const float *__restrict__ dy,
-        float dxt, float dyt, float dxh, float dyh, float dxb, float dyb)
+template <class M>
+__device__ __forceinline__ Interp3 interp3(double q_c, double q_e, double q_n, double q_en, long c, int r, int p,
+        const float *__restrict__ lu, const M &mt)
 {
     const long e = c + 1, no = c + p, en = c + 1 + p;
-    Interp3 r;
-    r.hu = f_interp2(q_c, q_e, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e], dxt, dyh);
-    r.hv = f_interp2(q_c, q_n, dx[c], dy[c], lu[c], dx[no], dy[no], lu[no], dxh, dyt);
-    r.hh = f_interp4(q_c, q_e, q_n, q_en, dx[c], dy[c], lu[c], dx[e], dy[e], lu[e],
-                     dx[no], dy[no], lu[no], dx[en], dy[en], lu[en], dxb, dyb);  // floats promote exactly
-    return r;
+    const double dx_c = mt.dx(c, r), dy_c = mt.dy(c, r), dx_e = mt.dx(e, r), dy_e = mt.dy(e, r);
+    const double dx_n = mt.dx(no, r + 1), dy_n = mt.dy(no, r + 1), dx_en = mt.dx(en, r + 1), dy_en = mt.dy(en, r + 1);
+    const double lu_c = (double)lu[c], lu_e = (double)lu[e], lu_n = (double)lu[no], lu_en = (double)lu[en];
+    Interp3 o;
+    // dble(lu+lu): the real(4) sum is exact for 0/1 masks and promotes exactly
+    const double su = hq_sum2(q_c, q_e, dx_c, dy_c, lu_c, dx_e, dy_e, lu_e);
+    const double sv = hq_sum2(q_c, q_n, dx_c, dy_c, lu_c, dx_n, dy_n, lu_n);
+    const double sh = q_c * dx_c * dy_c * lu_c + q_e * dx_e * dy_e * lu_e + q_n * dx_n * dy_n * lu_n
+                    + q_en * dx_en * dy_en * lu_en;
+    o.hu = dv<M>(dv<M>(div_slu_any(su, (double)(lu[c] + lu[e])), mt.dxt(c, r), mt.r_dxt(c, r)), mt.dyh(c, r), mt.r_dyh(c, r));
+    o.hv = dv<M>(dv<M>(div_slu_any(sv, (double)(lu[c] + lu[no])), mt.dxh(c, r), mt.r_dxh(c, r)), mt.dyt(c, r), mt.r_dyt(c, r));
+    o.hh = dv<M>(dv<M>(div_slu_any(sh, (double)(lu[c] + lu[e] + lu[no] + lu[en])), mt.dxb(c, r), mt.r_dxb(c, r)),
+                 mt.dyb(c, r), mt.r_dyb(c, r));
+    return o;
 }
 
 // K10 -- kernel/shallow_water/depth.f90:48-97
-__global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, double ffs,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, MetRow mr, double ffs,
         const float *__restrict__ lu, const float *__restrict__ llu, const float *__restrict__ llv,
         const float *__restrict__ luh,
         const float *__restrict__ dx, const float *__restrict__ dy,
@@ -188,19 +223,19 @@ __global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, double ffs,
     const long e = c + 1, no = c + p, en = c + 1 + p;
     const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
     if (!(wu || wv || wh)) return;
-    const float a = dxt[c], b = dyt[c], cc = dxh[c], d = dyh[c], ee = dxb[c], f = dyb[c];
-    const Interp3 i0 = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs,
-                              c, p, lu, dx, dy, a, b, cc, d, ee, f);
-    const Interp3 ip = interp3(qp, h_r[e] + shp[e] * ffs, h_r[no] + shp[no] * ffs, h_r[en] + shp[en] * ffs,
-                               c, p, lu, dx, dy, a, b, cc, d, ee, f);
-    const Interp3 in = interp3(qn, h_r[e], h_r[no], h_r[en], c, p, lu, dx, dy, a, b, cc, d, ee, f);
+    const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    const Interp3 i0 = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs, c, r, p, lu, mt);
+    const Interp3 ip = interp3(qp, h_r[e] + shp[e] * ffs, h_r[no] + shp[no] * ffs, h_r[en] + shp[en] * ffs, c, r, p, lu, mt);
+    const Interp3 in = interp3(qn, h_r[e], h_r[no], h_r[en], c, r, p, lu, mt);
     if (wu) { hu[c] = i0.hu; hup[c] = ip.hu; hun[c] = in.hu; }
     if (wv) { hv[c] = i0.hv; hvp[c] = ip.hv; hvn[c] = in.hv; }
     if (wh) { hh[c] = i0.hh; hhp[c] = ip.hh; hhn[c] = in.hh; }
 }
 
 // K2 -- kernel/shallow_water/depth.f90:129-160
-__global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g,
+template <bool ROW>
+__global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g, MetRow mr,
         const float *__restrict__ lu, const float *__restrict__ llu, const float *__restrict__ llv,
         const float *__restrict__ luh,
         const float *__restrict__ dx, const float *__restrict__ dy,
@@ -217,8 +252,9 @@ __global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g,
     const long e = c + 1, no = c + p, en = c + 1 + p;
     const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
     if (!(wu || wv || wh)) return;
-    const Interp3 in = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, p, lu, dx, dy,
-                               dxt[c], dyt[c], dxh[c], dyh[c], dxb[c], dyb[c]);
+    const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
+    const auto &mt = Pick<ROW>::get(mg, mr);
+    const Interp3 in = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, r, p, lu, mt);
     if (wu) hun[c] = in.hu;
     if (wv) hvn[c] = in.hv;
     if (wh) hhn[c] = in.hh;
@@ -316,9 +352,9 @@ const dim3 kBlock(BX, BY, 1);
 
 int launch_sw_update_ssh(const Geo &g, double tau, const float *lu, const float *dx, const float *dy,
         const float *dxh, const float *dyh, const double *hhu, const double *hhv, double *sshn,
-        const double *sshp, const double *u, const double *v, cudaStream_t st)
+        const double *sshp, const double *u, const double *v, cudaStream_t st, const MetRow *mr)
 {
-    k_sw_update_ssh<<<GRID_S, kBlock, 0, st>>>(g, tau, lu, dx, dy, dxh, dyh, hhu, hhv, sshn, sshp, u, v);
+    SWCU_LAUNCH_ROW(k_sw_update_ssh, GRID_S, tau, lu, dx, dy, dxh, dyh, hhu, hhv, sshn, sshp, u, v);
     return launched("sw_update_ssh");
 }
 
@@ -329,9 +365,10 @@ int launch_sw_update_uv(const Geo &g, double tau, const float *lcu, const float 
         const double *u, double *un, const double *up, const double *v, double *vn, const double *vp,
         const float *rdis, const float *rlh_s, const double *RHSx, const double *RHSy,
         const double *RHSx_adv, const double *RHSy_adv, const double *RHSx_dif, const double *RHSy_dif,
-        cudaStream_t st)
+        cudaStream_t st, const MetRow *mr, const Tau *tau_exact)
 {
-    k_sw_update_uv<<<GRID_S, kBlock, 0, st>>>(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb,
+    const Tau tt = tau_exact ? *tau_exact : Tau{tau, 0.0, 0, 0};  // plain Level A keeps the hardware division
+    SWCU_LAUNCH_ROW(k_sw_update_uv, GRID_S, tt, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb,
             hhu, hhun, hhup, hhv, hhvn, hhvp, hhh, ssh, u, un, up, v, vn, vp, rdis, rlh_s,
             RHSx, RHSy, RHSx_adv, RHSy_adv, RHSx_dif, RHSy_dif);
     return launched("sw_update_uv");
@@ -346,17 +383,17 @@ int launch_sw_next_step(const Geo &g, double ts, const float *lu, const float *l
 }
 
 int launch_uv_trans_vort(const Geo &g, const float *luu, const float *dxt, const float *dyt,
-        const float *dxb, const float *dyb, const double *u, const double *v, double *vort, cudaStream_t st)
+        const float *dxb, const float *dyb, const double *u, const double *v, double *vort, cudaStream_t st, const MetRow *mr)
 {
-    k_uv_trans_vort<<<GRID_S, kBlock, 0, st>>>(g, luu, dxt, dyt, dxb, dyb, u, v, vort);
+    SWCU_LAUNCH_ROW(k_uv_trans_vort, GRID_S, luu, dxt, dyt, dxb, dyb, u, v, vort);
     return launched("uv_trans_vort");
 }
 
 int launch_uv_trans(const Geo &g, const float *lcu, const float *lcv, const float *luu,
         const float *dxh, const float *dyh, const double *u, const double *v, const double *vort,
-        const double *hu, const double *hv, const double *hh, double *RHSx, double *RHSy, cudaStream_t st)
+        const double *hu, const double *hv, const double *hh, double *RHSx, double *RHSy, cudaStream_t st, const MetRow *mr)
 {
-    k_uv_trans<<<GRID_S, kBlock, 0, st>>>(g, lcu, lcv, luu, dxh, dyh, u, v, vort, hu, hv, hh, RHSx, RHSy);
+    SWCU_LAUNCH_ROW(k_uv_trans, GRID_S, lcu, lcv, luu, dxh, dyh, u, v, vort, hu, hv, hh, RHSx, RHSy);
     return launched("uv_trans");
 }
 
@@ -364,9 +401,9 @@ int launch_uv_diff2(const Geo &g, const float *lcu, const float *lcv,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
         const double *mu, const double *str_t, const double *str_s, const double *hq, const double *hh,
-        double *RHSx, double *RHSy, cudaStream_t st)
+        double *RHSx, double *RHSy, cudaStream_t st, const MetRow *mr)
 {
-    k_uv_diff2<<<GRID_S, kBlock, 0, st>>>(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+    SWCU_LAUNCH_ROW(k_uv_diff2, GRID_S, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
                                           mu, str_t, str_s, hq, hh, RHSx, RHSy);
     return launched("uv_diff2");
 }
@@ -374,9 +411,9 @@ int launch_uv_diff2(const Geo &g, const float *lcu, const float *lcv,
 int launch_stress_components(const Geo &g, const float *lu, const float *luu,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
-        const double *u, const double *v, double *str_t, double *str_s, cudaStream_t st)
+        const double *u, const double *v, double *str_t, double *str_s, cudaStream_t st, const MetRow *mr)
 {
-    k_stress_components<<<GRID_S, kBlock, 0, st>>>(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+    SWCU_LAUNCH_ROW(k_stress_components, GRID_S, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
                                                    u, v, str_t, str_s);
     return launched("stress_components");
 }
@@ -386,9 +423,9 @@ int launch_hh_init(const Geo &g, int ffs, const float *lu, const float *llu, con
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
         double *hq, double *hqp, double *hqn, double *hu, double *hup, double *hun,
         double *hv, double *hvp, double *hvn, double *hh, double *hhp, double *hhn,
-        const double *sh, const double *shp, const double *h_r, cudaStream_t st)
+        const double *sh, const double *shp, const double *h_r, cudaStream_t st, const MetRow *mr)
 {
-    k_hh_init<<<GRID_ALL, kBlock, 0, st>>>(g, (double)ffs, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+    SWCU_LAUNCH_ROW(k_hh_init, GRID_ALL, (double)ffs, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
             hq, hqp, hqn, hu, hup, hun, hv, hvp, hvn, hh, hhp, hhn, sh, shp, h_r);
     return launched("hh_init");
 }
@@ -396,9 +433,9 @@ int launch_hh_init(const Geo &g, int ffs, const float *lu, const float *llu, con
 int launch_hh_update(const Geo &g, const float *lu, const float *llu, const float *llv, const float *luh,
         const float *dx, const float *dy, const float *dxt, const float *dyt,
         const float *dxh, const float *dyh, const float *dxb, const float *dyb,
-        double *hqn, double *hun, double *hvn, double *hhn, const double *sh, const double *h_r, cudaStream_t st)
+        double *hqn, double *hun, double *hvn, double *hhn, const double *sh, const double *h_r, cudaStream_t st, const MetRow *mr)
 {
-    k_hh_update<<<GRID_ALL, kBlock, 0, st>>>(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+    SWCU_LAUNCH_ROW(k_hh_update, GRID_ALL, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
                                              hqn, hun, hvn, hhn, sh, h_r);
     return launched("hh_update");
 }
