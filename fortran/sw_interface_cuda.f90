@@ -7,7 +7,8 @@
 !
 !   swcuda_c_binding                      bind(C) interfaces of the C ABI
 !   shallow_water_interface_cuda_module   init_device_data_cuda, expl_shallow_water_cuda,
-!                                         download_ssh_cuda, finalize_device_data_cuda
+!                                         download_ssh_cuda, finalize_device_data_cuda, and the
+!                                         14 envoke_<name>_kernel_cuda / _sync_cuda pairs
 !
 ! One MPI rank drives one GPU and owns one block (parallel.par: bppnx = 1, bppny = 1 per rank on a
 ! 1 x nranks process grid, i.e. y-slabs).  Halo exchange happens inside swcu_step over NCCL.
@@ -30,6 +31,22 @@ module swcuda_c_binding
                                  SWCU_F_DX = 107, SWCU_F_DY = 108, SWCU_F_DXT = 109, SWCU_F_DYT = 110,   &
                                  SWCU_F_DXH = 111, SWCU_F_DYH = 112, SWCU_F_DXB = 113, SWCU_F_DYB = 114, &
                                  SWCU_F_RLH_S = 115, SWCU_F_R_DISS = 116
+
+    ! enum swcu_kernel (include/swcuda.h)
+    integer(c_int), parameter :: SWCU_K_SW_UPDATE_SSH = 1
+    integer(c_int), parameter :: SWCU_K_HH_UPDATE = 2
+    integer(c_int), parameter :: SWCU_K_UV_TRANS_VORT = 3
+    integer(c_int), parameter :: SWCU_K_UV_TRANS = 4
+    integer(c_int), parameter :: SWCU_K_STRESS_COMPONENTS = 5
+    integer(c_int), parameter :: SWCU_K_UV_DIFF2 = 6
+    integer(c_int), parameter :: SWCU_K_SW_UPDATE_UV = 7
+    integer(c_int), parameter :: SWCU_K_SW_NEXT_STEP = 8
+    integer(c_int), parameter :: SWCU_K_HH_SHIFT = 9
+    integer(c_int), parameter :: SWCU_K_HH_INIT = 10
+    integer(c_int), parameter :: SWCU_K_CHECK_SSH_ERR = 11
+    integer(c_int), parameter :: SWCU_K_TRAN_DIFF_FLUXES = 12
+    integer(c_int), parameter :: SWCU_K_TRAN_DIFF_TRACER = 13
+    integer(c_int), parameter :: SWCU_K_TRACER_NEXT_STEP = 14
 
     type, bind(C) :: swcu_dims
         integer(c_int) :: nx_start, nx_end, ny_start, ny_end
@@ -74,6 +91,19 @@ module swcuda_c_binding
         function swcu_envoke_hh_init(ctx) bind(C, name="swcu_envoke_hh_init") result(rc)
             import :: c_ptr, c_int
             type(c_ptr), value :: ctx
+            integer(c_int) :: rc
+        end function
+        function swcu_envoke_kernel(ctx, kernel_id, tau) bind(C, name="swcu_envoke_kernel") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: kernel_id
+            real(c_double), value :: tau
+            integer(c_int) :: rc
+        end function
+        function swcu_envoke_sync(ctx, kernel_id) bind(C, name="swcu_envoke_sync") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: kernel_id
             integer(c_int) :: rc
         end function
         function swcu_step(ctx, tau, nsteps) bind(C, name="swcu_step") result(rc)
@@ -123,6 +153,8 @@ module shallow_water_interface_cuda_module
     use grid_module, only: grid_type, grid_data
     use config_sw_module, only: full_free_surface, time_smooth, trans_terms, ksw_lat, use_tracers
     use errors_module, only: abort_model
+    use kernel_interface_module, only: kernel_parameters_type
+    use mpp_sync_module, only: sync_parameters_type
     implicit none
     save
     private
@@ -130,6 +162,20 @@ module shallow_water_interface_cuda_module
     type(c_ptr), allocatable :: ctx(:)      ! one resident context per local block
 
     public :: init_device_data_cuda, expl_shallow_water_cuda, download_ssh_cuda, finalize_device_data_cuda
+    public :: envoke_sw_update_ssh_kernel_cuda, envoke_sw_update_ssh_sync_cuda
+    public :: envoke_hh_update_kernel_cuda, envoke_hh_update_sync_cuda
+    public :: envoke_uv_trans_vort_kernel_cuda, envoke_uv_trans_vort_sync_cuda
+    public :: envoke_uv_trans_kernel_cuda, envoke_uv_trans_sync_cuda
+    public :: envoke_stress_components_kernel_cuda, envoke_stress_components_sync_cuda
+    public :: envoke_uv_diff2_kernel_cuda, envoke_uv_diff2_sync_cuda
+    public :: envoke_sw_update_uv_kernel_cuda, envoke_sw_update_uv_sync_cuda
+    public :: envoke_sw_next_step_kernel_cuda, envoke_sw_next_step_sync_cuda
+    public :: envoke_hh_shift_kernel_cuda, envoke_hh_shift_sync_cuda
+    public :: envoke_hh_init_kernel_cuda, envoke_hh_init_sync_cuda
+    public :: envoke_check_ssh_err_kernel_cuda, envoke_check_ssh_err_sync_cuda
+    public :: envoke_tran_diff_fluxes_kernel_cuda, envoke_tran_diff_fluxes_sync_cuda
+    public :: envoke_tran_diff_tracer_kernel_cuda, envoke_tran_diff_tracer_sync_cuda
+    public :: envoke_tracer_next_step_kernel_cuda, envoke_tracer_next_step_sync_cuda
 
 contains
 
@@ -217,6 +263,184 @@ contains
             call check(swcu_synchronize(ctx(k), bad), 'SIGFPRE predict error')
             call check(swcu_download(ctx(k), SWCU_F_SSH, c_loc(ocean_data%ssh%block(k)%field)), 'download')
         enddo
+    end subroutine
+
+    !------------------------------------------------------------------------------------------
+    ! Per-kernel route (SWCU_MODE_REFERENCE): procedures with the abstract interfaces
+    ! envoke_empty_kernel / envoke_empty_sync (core/kernel_interface.f90:38-46), so the reference's
+    ! expl_shallow_water / expl_tracer can keep their envoke(sub_kernel, sub_sync, parameters) calls
+    ! and only point sub_kernel / sub_sync at these instead of the CPU binders
+    ! (control/shallow_water/shallow_water.f90:36-92).  k = -1 in a sync means "all blocks"
+    ! (core/kernel_interface.f90:101).
+    !------------------------------------------------------------------------------------------
+    subroutine sync_all(kernel_id, k)
+        integer(c_int), intent(in) :: kernel_id
+        integer, intent(in) :: k
+        integer :: kk
+        if (k >= 1) then
+            call check(swcu_envoke_sync(ctx(k), kernel_id), 'sync')
+        else
+            !$omp master
+            do kk = 1, domain%bcount
+                call check(swcu_envoke_sync(ctx(kk), kernel_id), 'sync')
+            enddo
+            !$omp end master
+            !$omp barrier
+        endif
+    end subroutine
+
+    subroutine envoke_sw_update_ssh_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_SW_UPDATE_SSH, real(param%tau, c_double)), 'sw_update_ssh')
+    end subroutine
+    subroutine envoke_sw_update_ssh_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_SW_UPDATE_SSH, k)
+    end subroutine
+
+    subroutine envoke_hh_update_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_HH_UPDATE, real(param%tau, c_double)), 'hh_update')
+    end subroutine
+    subroutine envoke_hh_update_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_HH_UPDATE, k)
+    end subroutine
+
+    subroutine envoke_uv_trans_vort_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_UV_TRANS_VORT, real(param%tau, c_double)), 'uv_trans_vort')
+    end subroutine
+    subroutine envoke_uv_trans_vort_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_UV_TRANS_VORT, k)
+    end subroutine
+
+    subroutine envoke_uv_trans_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_UV_TRANS, real(param%tau, c_double)), 'uv_trans')
+    end subroutine
+    subroutine envoke_uv_trans_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_UV_TRANS, k)
+    end subroutine
+
+    subroutine envoke_stress_components_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_STRESS_COMPONENTS, real(param%tau, c_double)), 'stress_components')
+    end subroutine
+    subroutine envoke_stress_components_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_STRESS_COMPONENTS, k)
+    end subroutine
+
+    subroutine envoke_uv_diff2_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_UV_DIFF2, real(param%tau, c_double)), 'uv_diff2')
+    end subroutine
+    subroutine envoke_uv_diff2_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_UV_DIFF2, k)
+    end subroutine
+
+    subroutine envoke_sw_update_uv_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_SW_UPDATE_UV, real(param%tau, c_double)), 'sw_update_uv')
+    end subroutine
+    subroutine envoke_sw_update_uv_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_SW_UPDATE_UV, k)
+    end subroutine
+
+    subroutine envoke_sw_next_step_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_SW_NEXT_STEP, real(param%tau, c_double)), 'sw_next_step')
+    end subroutine
+    subroutine envoke_sw_next_step_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_SW_NEXT_STEP, k)
+    end subroutine
+
+    subroutine envoke_hh_shift_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_HH_SHIFT, real(param%tau, c_double)), 'hh_shift')
+    end subroutine
+    subroutine envoke_hh_shift_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_HH_SHIFT, k)
+    end subroutine
+
+    subroutine envoke_hh_init_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_HH_INIT, real(param%tau, c_double)), 'hh_init')
+    end subroutine
+    subroutine envoke_hh_init_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_HH_INIT, k)
+    end subroutine
+
+    subroutine envoke_check_ssh_err_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_CHECK_SSH_ERR, real(param%tau, c_double)), 'check_ssh_err')
+    end subroutine
+    subroutine envoke_check_ssh_err_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_CHECK_SSH_ERR, k)
+    end subroutine
+
+    subroutine envoke_tran_diff_fluxes_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_TRAN_DIFF_FLUXES, real(param%tau, c_double)), 'tran_diff_fluxes')
+    end subroutine
+    subroutine envoke_tran_diff_fluxes_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_TRAN_DIFF_FLUXES, k)
+    end subroutine
+
+    subroutine envoke_tran_diff_tracer_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_TRAN_DIFF_TRACER, real(param%tau, c_double)), 'tran_diff_tracer')
+    end subroutine
+    subroutine envoke_tran_diff_tracer_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_TRAN_DIFF_TRACER, k)
+    end subroutine
+
+    subroutine envoke_tracer_next_step_kernel_cuda(k, param)
+        integer, intent(in) :: k
+        type(kernel_parameters_type), intent(in) :: param
+        call check(swcu_envoke_kernel(ctx(k), SWCU_K_TRACER_NEXT_STEP, real(param%tau, c_double)), 'tracer_next_step')
+    end subroutine
+    subroutine envoke_tracer_next_step_sync_cuda(k, sync_parameters)
+        integer, intent(in) :: k
+        type(sync_parameters_type), intent(in) :: sync_parameters
+        call sync_all(SWCU_K_TRACER_NEXT_STEP, k)
     end subroutine
 
     subroutine finalize_device_data_cuda()

@@ -231,6 +231,24 @@ int swcu_uses_metric_tables(const swcu_ctx *ctx);
  * depth fields are functions of the resident state. */
 int swcu_envoke_hh_init(swcu_ctx *ctx);
 
+/* Kernel ids for the per-kernel envokes below: the (kernel, sync) pairs expl_shallow_water and
+ * expl_tracer hand to envoke (control/shallow_water/shallow_water.f90:36-92, control/tracer.f90:50-60). */
+enum swcu_kernel {
+    SWCU_K_SW_UPDATE_SSH = 1, SWCU_K_HH_UPDATE, SWCU_K_UV_TRANS_VORT, SWCU_K_UV_TRANS,
+    SWCU_K_STRESS_COMPONENTS, SWCU_K_UV_DIFF2, SWCU_K_SW_UPDATE_UV, SWCU_K_SW_NEXT_STEP,
+    SWCU_K_HH_SHIFT, SWCU_K_HH_INIT, SWCU_K_CHECK_SSH_ERR,
+    SWCU_K_TRAN_DIFF_FLUXES, SWCU_K_TRAN_DIFF_TRACER, SWCU_K_TRACER_NEXT_STEP
+};
+/* envoke_<name>_kernel(k, param) / envoke_<name>_sync(k, sync_parameters) of
+ * interface/shallow_water/sw_interface.f90:42-408 and interface/tracer/tracer_interface.f90:28-102 on
+ * the context's RESIDENT arrays (SWCU_MODE_REFERENCE): the binder's choice of arrays, then the 1:1
+ * kernel; the sync exchanges the fields that binder's sync lists (width 1) with the neighbouring
+ * blocks when a communicator is attached, else it is a no-op like a one-block hybrid_sync.  With these
+ * two the reference's algorithm layer can keep its own envoke(sub_kernel, sub_sync, parameters)
+ * sequence unchanged and still run on the device. */
+int swcu_envoke_kernel(swcu_ctx *ctx, int kernel_id, double tau);
+int swcu_envoke_sync(swcu_ctx *ctx, int kernel_id);
+
 /* nsteps x expl_shallow_water(tau) [+ expl_tracer(tau) when use_tracers], asynchronous on the
  * context's stream; no host round trip.  With a communicator attached (below) every step
  * exchanges halos with the neighbouring blocks. */

@@ -21,6 +21,9 @@ F4_NAMES = ["lu", "luu", "luh", "lcu", "lcv", "llu", "llv",
 FIELD_ID = {n: i for i, n in enumerate(F8_NAMES)}
 FIELD_ID.update({n: 100 + i for i, n in enumerate(F4_NAMES)})
 MASK_NAMES = F4_NAMES[:7]
+KERNEL_ID = {n: i + 1 for i, n in enumerate([
+    "sw_update_ssh", "hh_update", "uv_trans_vort", "uv_trans", "stress_components", "uv_diff2", "sw_update_uv",
+    "sw_next_step", "hh_shift", "hh_init", "check_ssh_err", "tran_diff_fluxes", "tran_diff_tracer", "tracer_next_step"])}
 
 
 class SwcuDims(C.Structure):
@@ -84,6 +87,8 @@ _SIGNATURES = {
     "swcu_set_option": [_P, C.c_char_p, _I],
     "swcu_uses_metric_tables": [_P],
     "swcu_envoke_hh_init": [_P],
+    "swcu_envoke_kernel": [_P, _I, _D],
+    "swcu_envoke_sync": [_P, _I],
     "swcu_step": [_P, _D, _I],
     "swcu_synchronize": [_P, C.POINTER(C.c_long)],
     "swcu_timer_start": [_P],

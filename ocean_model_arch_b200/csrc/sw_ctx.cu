@@ -251,9 +251,10 @@ int prof_mark(swcu_ctx *c, int kind, bool begin, cudaStream_t st = nullptr)
 
 int prepare_metrics(swcu_ctx *c);
 
-// control/shallow_water/shallow_water.f90:22-94 with the binders' argument choice
-// (interface/shallow_water/sw_interface.f90), then control/tracer.f90:44-61
-int step_reference(swcu_ctx *c, double tau)
+// One envoke_<name>_kernel(k, param) of interface/shallow_water/sw_interface.f90:42-403 (and
+// interface/tracer/tracer_interface.f90:28-96) on the context's resident arrays: the binder's choice of
+// which ocean_data / grid_data array goes to which dummy argument, then the 1:1 kernel.
+int envoke_kernel(swcu_ctx *c, int kid, double tau)
 {
     const Geo &g = c->g;
     cudaStream_t st = c->st;
@@ -268,75 +269,110 @@ int step_reference(swcu_ctx *c, double tau)
     if (c->metrics_dirty) RC(prepare_metrics(c));
     const MetRow mrow{c->tab, c->h, 0};
     const MetRow *mr = c->use_tables ? &mrow : nullptr;
-    Tau tt;
-    {
-        int ex = 0;
-        const double mant = frexp(tau, &ex);
-        tt.tau = tau; tt.rtau = 1.0 / tau; tt.pow2 = (mant == 0.5 && tau > 1e-300 && tau < 1e300) ? 1 : 0; tt.exact = 1;
+    c->launches++;
+    switch (kid) {
+        case SWCU_K_SW_UPDATE_SSH:  // sw_interface.f90:310-328
+            return launch_sw_update_ssh(g, tau, lu, dx, dy, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_SSHN],
+                                        F[SWCU_F_SSHP], F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], st, mr);
+        case SWCU_K_HH_UPDATE:  // :145-169 (takes ssh)
+            return launch_hh_update(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHQ_N],
+                                    F[SWCU_F_HHU_N], F[SWCU_F_HHV_N], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_HHQ_REST],
+                                    st, mr);
+        case SWCU_K_UV_TRANS_VORT:  // :211-229
+            return launch_uv_trans_vort(g, luu, dxt, dyt, dxb, dyb, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT], st, mr);
+        case SWCU_K_UV_TRANS:  // :238-262
+            return launch_uv_trans(g, lcu, lcv, luu, dxh, dyh, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT],
+                                   F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_HHH], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV], st, mr);
+        case SWCU_K_STRESS_COMPONENTS:  // :110-134 (takes ubrtrp, vbrtrp)
+            return launch_stress_components(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_UBRTRP],
+                                            F[SWCU_F_VBRTRP], F[SWCU_F_STR_T], F[SWCU_F_STR_S], st, mr);
+        case SWCU_K_UV_DIFF2:  // :273-302
+            return launch_uv_diff2(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_MU], F[SWCU_F_STR_T],
+                                   F[SWCU_F_STR_S], F[SWCU_F_HHQ], F[SWCU_F_HHH], F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr);
+        case SWCU_K_SW_UPDATE_UV: {  // :337-374
+            Tau tt;
+            int ex = 0;
+            const double mant = frexp(tau, &ex);
+            tt.tau = tau; tt.rtau = 1.0 / tau; tt.pow2 = (mant == 0.5 && tau > 1e-300 && tau < 1e300) ? 1 : 0; tt.exact = 1;
+            return launch_sw_update_uv(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHU], F[SWCU_F_HHU_N],
+                                       F[SWCU_F_HHU_P], F[SWCU_F_HHV], F[SWCU_F_HHV_N], F[SWCU_F_HHV_P], F[SWCU_F_HHH],
+                                       F[SWCU_F_SSH], F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR],
+                                       F[SWCU_F_VBRTRN], F[SWCU_F_VBRTRP], F4(c, SWCU_F_R_DISS), F4(c, SWCU_F_RLH_S),
+                                       F[SWCU_F_RHSX], F[SWCU_F_RHSY], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV],
+                                       F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr, &tt);
+        }
+        case SWCU_K_SW_NEXT_STEP:  // :384-403
+            return launch_sw_next_step(g, p.time_smooth, lu, lcu, lcv, F[SWCU_F_SSH], F[SWCU_F_SSHN], F[SWCU_F_SSHP],
+                                       F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR],
+                                       F[SWCU_F_VBRTRN], F[SWCU_F_VBRTRP], st);
+        case SWCU_K_HH_SHIFT:  // :181-203
+            return launch_hh_shift(g, p.time_smooth, lu, llu, llv, luh, F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N],
+                                   F[SWCU_F_HHU], F[SWCU_F_HHU_P], F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P],
+                                   F[SWCU_F_HHV_N], F[SWCU_F_HHH], F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], st);
+        case SWCU_K_HH_INIT:  // :42-75
+            return launch_hh_init(g, p.full_free_surface, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
+                                  F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
+                                  F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
+                                  F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], st, mr);
+        case SWCU_K_CHECK_SSH_ERR:  // :93-102
+            return launch_check_ssh_err(g, lu, F[SWCU_F_SSH], c->bad_dev, st);
+        case SWCU_K_TRAN_DIFF_FLUXES:  // tracer_interface.f90:28-49
+            if (!p.use_tracers) break;
+            return launch_tran_diff_fluxes(g, lcu, lcv, dxt, dyt, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_FF1],
+                                           F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_MU], 1.0, F[SWCU_F_FLUX_X],
+                                           F[SWCU_F_FLUX_Y], st);
+        case SWCU_K_TRAN_DIFF_TRACER:  // :59-74
+            if (!p.use_tracers) break;
+            return launch_tran_diff_tracer(g, lu, dx, dy, tau, F[SWCU_F_HHQ_N], F[SWCU_F_HHQ_P], F[SWCU_F_FLUX_X],
+                                           F[SWCU_F_FLUX_Y], F[SWCU_F_FF1P], F[SWCU_F_FF1N], st);
+        case SWCU_K_TRACER_NEXT_STEP:  // :83-96
+            if (!p.use_tracers) break;
+            return launch_tracer_next_step(g, p.time_smooth, lu, F[SWCU_F_FF1N], F[SWCU_F_FF1P], F[SWCU_F_FF1], st);
+        default: break;
     }
+    c->launches--;
+    set_error("unknown kernel id %d (or tracer kernel without use_tracers)", kid);
+    return SWCU_ERR_ARG;
+}
 
-    RC(launch_sw_update_ssh(g, tau, lu, dx, dy, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_SSHN],
-                            F[SWCU_F_SSHP], F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], st, mr));
-    c->launches++;
-    RC(sync_fields(c, {SWCU_F_SSHN}));
-    if (p.full_free_surface > 0) {
-        RC(launch_hh_update(g, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHQ_N],
-                            F[SWCU_F_HHU_N], F[SWCU_F_HHV_N], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_HHQ_REST], st, mr));
-        c->launches++;
-        RC(sync_fields(c, {SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N}));
+// The matching envoke_<name>_sync (sw_interface.f90:77-408, tracer_interface.f90:51-102): which fields
+// are halo-synced after the kernel (width 1, like hybrid_sync).
+int envoke_sync(swcu_ctx *c, int kid)
+{
+    switch (kid) {
+        case SWCU_K_SW_UPDATE_SSH: return sync_fields(c, {SWCU_F_SSHN});
+        case SWCU_K_HH_UPDATE: return sync_fields(c, {SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N});
+        case SWCU_K_UV_TRANS_VORT: return sync_fields(c, {SWCU_F_VORT});
+        case SWCU_K_UV_TRANS: return sync_fields(c, {SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P});  // "lazy"
+        case SWCU_K_STRESS_COMPONENTS: return sync_fields(c, {SWCU_F_STR_T, SWCU_F_STR_S});
+        case SWCU_K_SW_UPDATE_UV: return sync_fields(c, {SWCU_F_VBRTRN, SWCU_F_UBRTRN});
+        case SWCU_K_HH_INIT: return sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH});
+        case SWCU_K_TRAN_DIFF_FLUXES: return sync_fields(c, {SWCU_F_FLUX_X, SWCU_F_FLUX_Y});
+        case SWCU_K_TRAN_DIFF_TRACER: return sync_fields(c, {SWCU_F_FF1N});
+        case SWCU_K_UV_DIFF2: case SWCU_K_SW_NEXT_STEP: case SWCU_K_HH_SHIFT: case SWCU_K_CHECK_SSH_ERR:
+        case SWCU_K_TRACER_NEXT_STEP: return SWCU_OK;  // empty syncs in the reference
+        default: set_error("unknown kernel id %d", kid); return SWCU_ERR_ARG;
     }
-    if (p.trans_terms > 0) {
-        RC(launch_uv_trans_vort(g, luu, dxt, dyt, dxb, dyb, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT], st, mr));
-        RC(sync_fields(c, {SWCU_F_VORT}));
-        RC(launch_uv_trans(g, lcu, lcv, luu, dxh, dyh, F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_VORT],
-                           F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_HHH], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV], st, mr));
-        c->launches += 2;
-        RC(sync_fields(c, {SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P}));
-    }
-    if (p.ksw_lat > 0) {
-        RC(launch_stress_components(g, lu, luu, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_UBRTRP],
-                                    F[SWCU_F_VBRTRP], F[SWCU_F_STR_T], F[SWCU_F_STR_S], st, mr));
-        RC(sync_fields(c, {SWCU_F_STR_T, SWCU_F_STR_S}));
-        RC(launch_uv_diff2(g, lcu, lcv, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_MU], F[SWCU_F_STR_T],
-                           F[SWCU_F_STR_S], F[SWCU_F_HHQ], F[SWCU_F_HHH], F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr));
-        c->launches += 2;
-    }
-    RC(launch_sw_update_uv(g, tau, lcu, lcv, dxt, dyt, dxh, dyh, dxb, dyb, F[SWCU_F_HHU], F[SWCU_F_HHU_N],
-                           F[SWCU_F_HHU_P], F[SWCU_F_HHV], F[SWCU_F_HHV_N], F[SWCU_F_HHV_P], F[SWCU_F_HHH],
-                           F[SWCU_F_SSH], F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR],
-                           F[SWCU_F_VBRTRN], F[SWCU_F_VBRTRP], F4(c, SWCU_F_R_DISS), F4(c, SWCU_F_RLH_S),
-                           F[SWCU_F_RHSX], F[SWCU_F_RHSY], F[SWCU_F_RHSX_ADV], F[SWCU_F_RHSY_ADV],
-                           F[SWCU_F_RHSX_DIF], F[SWCU_F_RHSY_DIF], st, mr, &tt));
-    c->launches++;
-    RC(sync_fields(c, {SWCU_F_VBRTRN, SWCU_F_UBRTRN}));
-    RC(launch_sw_next_step(g, p.time_smooth, lu, lcu, lcv, F[SWCU_F_SSH], F[SWCU_F_SSHN], F[SWCU_F_SSHP],
-                           F[SWCU_F_UBRTR], F[SWCU_F_UBRTRN], F[SWCU_F_UBRTRP], F[SWCU_F_VBRTR], F[SWCU_F_VBRTRN],
-                           F[SWCU_F_VBRTRP], st));
-    c->launches++;
-    if (p.full_free_surface > 0) {
-        RC(launch_hh_shift(g, p.time_smooth, lu, llu, llv, luh, F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N],
-                           F[SWCU_F_HHU], F[SWCU_F_HHU_P], F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P],
-                           F[SWCU_F_HHV_N], F[SWCU_F_HHH], F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], st));
-        RC(launch_hh_init(g, p.full_free_surface, lu, llu, llv, luh, dx, dy, dxt, dyt, dxh, dyh, dxb, dyb,
-                          F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
-                          F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
-                          F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], st, mr));
-        c->launches += 2;
-        RC(sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH}));
-    }
-    RC(launch_check_ssh_err(g, lu, F[SWCU_F_SSH], c->bad_dev, st));
-    c->launches++;
+}
 
+#define ENVOKE(kid) do { RC(envoke_kernel(c, kid, tau)); RC(envoke_sync(c, kid)); } while (0)
+
+// control/shallow_water/shallow_water.f90:22-94, then control/tracer.f90:44-61
+int step_reference(swcu_ctx *c, double tau)
+{
+    const swcu_params &p = c->p;
+    ENVOKE(SWCU_K_SW_UPDATE_SSH);
+    if (p.full_free_surface > 0) ENVOKE(SWCU_K_HH_UPDATE);
+    if (p.trans_terms > 0) { ENVOKE(SWCU_K_UV_TRANS_VORT); ENVOKE(SWCU_K_UV_TRANS); }
+    if (p.ksw_lat > 0) { ENVOKE(SWCU_K_STRESS_COMPONENTS); ENVOKE(SWCU_K_UV_DIFF2); }
+    ENVOKE(SWCU_K_SW_UPDATE_UV);
+    ENVOKE(SWCU_K_SW_NEXT_STEP);
+    if (p.full_free_surface > 0) { ENVOKE(SWCU_K_HH_SHIFT); ENVOKE(SWCU_K_HH_INIT); }
+    ENVOKE(SWCU_K_CHECK_SSH_ERR);
     if (p.use_tracers > 0) {
-        RC(launch_tran_diff_fluxes(g, lcu, lcv, dxt, dyt, dxh, dyh, F[SWCU_F_HHU], F[SWCU_F_HHV], F[SWCU_F_FF1],
-                                   F[SWCU_F_UBRTR], F[SWCU_F_VBRTR], F[SWCU_F_MU], 1.0, F[SWCU_F_FLUX_X],
-                                   F[SWCU_F_FLUX_Y], st));
-        RC(sync_fields(c, {SWCU_F_FLUX_X, SWCU_F_FLUX_Y}));
-        RC(launch_tran_diff_tracer(g, lu, dx, dy, tau, F[SWCU_F_HHQ_N], F[SWCU_F_HHQ_P], F[SWCU_F_FLUX_X],
-                                   F[SWCU_F_FLUX_Y], F[SWCU_F_FF1P], F[SWCU_F_FF1N], st));
-        RC(sync_fields(c, {SWCU_F_FF1N}));
-        RC(launch_tracer_next_step(g, p.time_smooth, lu, F[SWCU_F_FF1N], F[SWCU_F_FF1P], F[SWCU_F_FF1], st));
-        c->launches += 3;
+        ENVOKE(SWCU_K_TRAN_DIFF_FLUXES);
+        ENVOKE(SWCU_K_TRAN_DIFF_TRACER);
+        ENVOKE(SWCU_K_TRACER_NEXT_STEP);
     }
     return SWCU_OK;
 }
@@ -836,17 +872,26 @@ int swcu_envoke_hh_init(swcu_ctx *c)
     if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
     if (c->p.mode == SWCU_MODE_FUSED) return SWCU_OK;
     Use use(c->device);
-    double **F = c->f8;
-    RC(launch_hh_init(c->g, c->p.full_free_surface, F4(c, SWCU_F_LU), F4(c, SWCU_F_LLU), F4(c, SWCU_F_LLV),
-                      F4(c, SWCU_F_LUH), F4(c, SWCU_F_DX), F4(c, SWCU_F_DY), F4(c, SWCU_F_DXT), F4(c, SWCU_F_DYT),
-                      F4(c, SWCU_F_DXH), F4(c, SWCU_F_DYH), F4(c, SWCU_F_DXB), F4(c, SWCU_F_DYB),
-                      F[SWCU_F_HHQ], F[SWCU_F_HHQ_P], F[SWCU_F_HHQ_N], F[SWCU_F_HHU], F[SWCU_F_HHU_P],
-                      F[SWCU_F_HHU_N], F[SWCU_F_HHV], F[SWCU_F_HHV_P], F[SWCU_F_HHV_N], F[SWCU_F_HHH],
-                      F[SWCU_F_HHH_P], F[SWCU_F_HHH_N], F[SWCU_F_SSH], F[SWCU_F_SSHP], F[SWCU_F_HHQ_REST], c->st));
-    c->launches++;
-    RC(sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH}));
+    RC(envoke_kernel(c, SWCU_K_HH_INIT, 0.0));
+    RC(envoke_sync(c, SWCU_K_HH_INIT));
     SWCU_CUDA(cudaStreamSynchronize(c->st));
     return SWCU_OK;
+}
+
+int swcu_envoke_kernel(swcu_ctx *c, int kernel_id, double tau)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_REFERENCE) { set_error("per-kernel envokes need SWCU_MODE_REFERENCE"); return SWCU_ERR_STATE; }
+    Use use(c->device);
+    return envoke_kernel(c, kernel_id, tau);
+}
+
+int swcu_envoke_sync(swcu_ctx *c, int kernel_id)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_REFERENCE) { set_error("per-kernel envokes need SWCU_MODE_REFERENCE"); return SWCU_ERR_STATE; }
+    Use use(c->device);
+    return envoke_sync(c, kernel_id);
 }
 
 int swcu_step(swcu_ctx *c, double tau, int nsteps)

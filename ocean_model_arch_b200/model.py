@@ -267,6 +267,13 @@ class DeviceBlock:
     def step(self, tau, nsteps=1):
         check(self.L.swcu_step(self.h, float(tau), int(nsteps)))
 
+    def envoke(self, kernel, tau=0.0):
+        """envoke(sub_kernel, sub_sync, kernel_parameters) for one (kernel, sync) pair on the resident
+        arrays (core/kernel_interface.f90:48-119), REFERENCE mode."""
+        kid = _lib.KERNEL_ID[kernel]
+        check(self.L.swcu_envoke_kernel(self.h, kid, float(tau)))
+        check(self.L.swcu_envoke_sync(self.h, kid))
+
     def set_option(self, name, value):
         check(self.L.swcu_set_option(self.h, name.encode(), int(value)))
 
@@ -360,6 +367,32 @@ class ShallowWaterModel:
         self.num_step += nsteps
 
     step = expl_shallow_water
+
+    def expl_shallow_water_envokes(self):
+        """The reference's own algorithm layer, statement by statement (control/shallow_water/
+        shallow_water.f90:22-94 then control/tracer.f90:33-62): every (kernel, sync) pair is envoked
+        through the C ABI on the resident arrays.  REFERENCE mode only."""
+        sw, e, tau = self.sw, self.block.envoke, self.tau
+        e("sw_update_ssh", tau)
+        if sw.full_free_surface > 0:
+            e("hh_update")
+        if sw.trans_terms > 0:
+            e("uv_trans_vort")
+            e("uv_trans")
+        if sw.ksw_lat > 0:
+            e("stress_components")
+            e("uv_diff2")
+        e("sw_update_uv", tau)
+        e("sw_next_step")
+        if sw.full_free_surface > 0:
+            e("hh_shift")
+            e("hh_init")
+        e("check_ssh_err")
+        if sw.use_tracers > 0:
+            e("tran_diff_fluxes")
+            e("tran_diff_tracer", tau)
+            e("tracer_next_step")
+        self.num_step += 1
 
     def get(self, name):
         return self.block.download(name)

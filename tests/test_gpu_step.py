@@ -345,3 +345,23 @@ def test_all_land_tiles_are_skipped_safely(swlib, cuda_device):
     for f in STATE:
         assert np.array_equal(a.get(f), o.get(f)), f
     assert (a.get("ssh")[mask == 1] == 7.0).all()
+
+
+def test_reference_algorithm_layer_through_envokes(swlib, cuda_device):
+    """The drop-in boundary as the reference uses it: expl_shallow_water / expl_tracer written as
+    the reference writes them -- a sequence of envoke(kernel, sync) pairs -- with every pair going
+    through swcu_envoke_kernel / swcu_envoke_sync on the resident arrays."""
+    nx, ny = 81, 64
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, use_tracers=1, keep_mu=1), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), model.SwPar(use_tracers=1), mask=mask,
+                                mode=MODE_REFERENCE, keep_mu=True)
+    for _ in range(12):
+        m.expl_shallow_water_envokes()
+    o.step(12)
+    assert m.block.synchronize() == 0
+    for f in STATE + ("ff1", "ff1p", "hhu", "hhq_p", "vort", "RHSx_adv", "RHSy_dif", "flux_x"):
+        assert np.array_equal(m.get(f), o.get(f)), f
+    fused = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED)
+    with pytest.raises(Exception):
+        fused.block.envoke("sw_update_ssh", 1.0)
