@@ -266,6 +266,11 @@ int swcu_timer_stop(swcu_ctx *ctx, float *elapsed_ms);
  * (prep, update).  FUSED mode only; used for per-kernel roofline numbers. */
 int swcu_profile_steps(swcu_ctx *ctx, double tau, int nsteps,
                        float *prep_ms, long *prep_launches, float *update_ms, long *update_launches);
+/* Self-test of the exact division used by the fused kernels: on `n` pseudo-random operand pairs
+ * (dividends of both signs over 2^-200..2^200 incl. zeros of both signs, divisors = real(4) values
+ * promoted to double like the metric arrays, and arbitrary doubles) compares mdiv(a, b, RN(1/b)) with
+ * the IEEE division a/b BITWISE on the device and returns the number of mismatches. */
+int swcu_selftest_mdiv(long n, unsigned long long seed, long *mismatches);
 /* Launch count of this library's kernels on this context since creation. */
 long swcu_launch_count(const swcu_ctx *ctx);
 /* Bytes of device memory held by the context. */

@@ -94,6 +94,7 @@ _SIGNATURES = {
     "swcu_timer_start": [_P],
     "swcu_timer_stop": [_P, C.POINTER(C.c_float)],
     "swcu_profile_steps": [_P, _D, _I, C.POINTER(C.c_float), C.POINTER(C.c_long), C.POINTER(C.c_float), C.POINTER(C.c_long)],
+    "swcu_selftest_mdiv": [C.c_long, C.c_ulonglong, C.POINTER(C.c_long)],
     "swcu_launch_count": [_P],
     "swcu_device_bytes": [_P],
     "swcu_stream": [_P],

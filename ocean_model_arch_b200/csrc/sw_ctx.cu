@@ -964,6 +964,22 @@ int swcu_timer_stop(swcu_ctx *c, float *ms)
     SWCU_CUDA(cudaEventElapsedTime(ms, c->t0, c->t1));
     return SWCU_OK;
 }
+int swcu_selftest_mdiv(long n, unsigned long long seed, long *mismatches)
+{
+    if (n < 1 || !mismatches) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    unsigned long long *bad = nullptr, host = 0;
+    SWCU_CUDA(cudaMalloc((void **)&bad, sizeof(*bad)));
+    SWCU_CUDA(cudaMemset(bad, 0, sizeof(*bad)));
+    int rc = launch_selftest_mdiv(n, seed, bad, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "selftest copy");
+    }
+    cudaFree(bad);
+    *mismatches = (long)host;
+    return rc;
+}
+
 long swcu_launch_count(const swcu_ctx *c) { return c ? c->launches : 0; }
 long swcu_device_bytes(const swcu_ctx *c) { return c ? c->bytes : 0; }
 void *swcu_stream(swcu_ctx *c) { return c ? (void *)c->st : nullptr; }

@@ -60,6 +60,7 @@ int launch_tracer(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t
 // fp32 output record of the interior with undef on land (either a mask byte plane or a real(4) lu)
 int launch_output_record(const Geo &g, const double *field, const unsigned char *mask_bits, const float *lu,
                          float *out, cudaStream_t st);
+int launch_selftest_mdiv(long n, unsigned long long seed, unsigned long long *bad_dev, cudaStream_t st);
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 

@@ -464,6 +464,47 @@ int launch_output_record(const Geo &g, const double *field, const unsigned char 
     return launched("output_record");
 }
 
+// ---- self-test of mdiv ---------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long &x)
+{
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// a double with random sign and mantissa and an exponent in [-span, span]
+__device__ __forceinline__ double rnd_double(unsigned long long &st, int span)
+{
+    const unsigned long long r = splitmix(st);
+    const long long e = 1023 + (long long)(splitmix(st) % (unsigned long long)(2 * span + 1)) - span;
+    return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | ((unsigned long long)e << 52)));
+}
+__global__ void k_selftest_mdiv(long n, unsigned long long seed, unsigned long long *bad)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long st = seed + 0x632be59bd9b4e019ull * (unsigned long long)(i + 1);
+    double a = rnd_double(st, 200);
+    const unsigned sel = (unsigned)(splitmix(st) & 7u);
+    if (sel == 0) a = 0.0;
+    if (sel == 1) a = -0.0;
+    double b;
+    if (splitmix(st) & 1ull) b = (double)(float)rnd_double(st, 60);   // like a promoted real(4) metric
+    else b = rnd_double(st, 200);
+    if (splitmix(st) & 1ull) b = fabs(b);
+    const double y = 1.0 / b;
+    const double q = mdiv(a, b, y), want = a / b;
+    if (__double_as_longlong(q) != __double_as_longlong(want)) atomicAdd(bad, 1ull);
+}
+}  // namespace
+
+int launch_selftest_mdiv(long n, unsigned long long seed, unsigned long long *bad_dev, cudaStream_t st)
+{
+    k_selftest_mdiv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, bad_dev);
+    return launched("selftest_mdiv");
+}
+
 // ---- mask packing -----------------------------------------------------------------------------
 namespace {
 __global__ void k_mask_set(long total, const float *__restrict__ src, unsigned char *__restrict__ bits, int bit)

@@ -144,3 +144,15 @@ def test_check_ssh_err_counts(swlib, cuda_device, state):
                                           C.c_void_p(bad.data_ptr()), None))
     torch.cuda.synchronize()
     assert int(bad.item()) == want
+
+
+@pytest.mark.parametrize("seed", [1, 2024, 987654321])
+def test_mdiv_is_ieee_division(swlib, cuda_device, seed):
+    """The exact division of the fused kernels (q0 = a*y, two FMA residual corrections with y = RN(1/b),
+    sign bit from q0) against the hardware IEEE division, bitwise, on 2^26 random operand pairs per
+    seed: dividends over 2^-200..2^200 of both signs incl. +-0, divisors both promoted real(4) values and
+    arbitrary doubles."""
+    bad = C.c_long(-1)
+    from ocean_model_arch_b200._lib import check
+    check(swlib.swcu_selftest_mdiv(1 << 26, seed, C.byref(bad)))
+    assert bad.value == 0
