@@ -102,3 +102,48 @@ def test_fast_build_stays_within_tolerance():
     for f in ("ssh", "ubrtr", "vbrtr"):
         x, y = a.get(f), b.get(f)
         assert np.linalg.norm(x - y) <= 1e-12 * np.linalg.norm(x), f
+
+
+def test_linear_gravity_mode_known_answer():
+    """A known-answer test that does NOT come from reading the reference's code: with transport,
+    viscosity, Coriolis, the free-surface depth correction and the time filter switched off, the scheme
+    is the classical leapfrog C-grid discretisation of the linear shallow-water equations.  For a
+    standing eigenmode cos(p pi x/Lx) cos(q pi y/Ly) of the closed flat basin, eliminating u and v
+    between two consecutive steps gives the exact three-level identity
+        ssh(n+2) - 2 ssh(n) + ssh(n-2) = -4 tau^2 g H Lambda ssh(n),
+        Lambda = (2 sin(p pi/(2 Nx))/dx)^2 + (2 sin(q pi/(2 Ny))/dy)^2,
+    to rounding -- except that K1 divides by the REAL(4) product dx*dy (kernel/shallow_water/vel_ssh.f90:100),
+    so Lambda carries the factor dx*dy / real4(dx*dy); the test resolves that 5e-8 effect.
+    It pins the divergence and cell-area factor of K1, the pressure gradient and the
+    bp/bp0 bookkeeping of K7, the level rotation of K8 and the wall masks."""
+    nx, ny, p, q = 68, 52, 2, 1
+    Nx, Ny = nx - 4, ny - 4
+    tau = 5.0
+    m = OracleModel(make_config(nx, ny, curve_grid=0, dxst=0.01, dyst=0.01, full_free_surface=0, trans_terms=0,
+                                ksw_lat=0, time_smooth=0.0, time_step=tau), None)
+    m.set("rlh_s", np.zeros((ny, nx), np.float32))
+    dx = float(m.get("dx")[10, 10]); dy = float(m.get("dy")[10, 10])
+    jj, ii = np.mgrid[1:ny + 1, 1:nx + 1]
+    phi = np.cos(p * np.pi * (ii - 2.5) / Nx) * np.cos(q * np.pi * (jj - 2.5) / Ny)   # cell centres
+    phi[m.get("lu") < 0.5] = 0.0
+    for f in ("ssh", "sshp", "sshn"):
+        m.set(f, 0.1 * phi)
+    a = []
+    sea = m.get("lu") > 0.5
+    for _ in range(400):
+        a.append(float((m.get("ssh")[sea] * phi[sea]).sum() / (phi[sea] ** 2).sum()))
+        # the state stays in the one-dimensional eigenspace (up to rounding)
+        m.step(1)
+    a = np.array(a)
+    resid = m.get("ssh") - a[-1] * phi
+    g = float(np.float32(9.8)); H = 100.0
+    lam = (2 * np.sin(p * np.pi / (2 * Nx)) / dx) ** 2 + (2 * np.sin(q * np.pi / (2 * Ny)) / dy) ** 2
+    area4 = float(np.float32(dx) * np.float32(dy))                # the real(4) product K1 divides by
+    want = -4 * tau ** 2 * g * H * lam * (dx * dy / area4)
+    assert abs(dx * dy / area4 - 1) > 1e-9                         # (and the test can tell the difference)
+    n = np.arange(2, len(a) - 2)
+    big = np.abs(a[n]) > 0.02
+    got = (a[n + 2] - 2 * a[n] + a[n - 2])[big] / a[n][big]
+    assert np.abs(got - want).max() < 1e-9 * abs(want) + 1e-11, (got.min(), got.max(), want)
+    assert 0.05 < np.abs(a).max() < 0.1 * 1.001                  # neutral: no growth (the start excites a tiny computational mode)
+    assert np.sign(a).min() < 0 < np.sign(a).max()               # it really oscillates
