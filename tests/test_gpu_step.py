@@ -111,6 +111,14 @@ def test_fused_equals_reference_sequence_at_2048(swlib, cuda_device):
         assert np.array_equal(x, y), f
         assert np.isfinite(x).all()
     assert b.block.launches == 20 and a.block.launches == 20 * 11 + 1   # one TMA-tiled launch per step
+    # size-independent properties at the full size: mass is conserved (K1 is in flux form; the weight
+    # is the real(4) product dx*dy it divides by), the land frame is untouched, |ssh| stays bounded
+    area = (b.get("dx") * b.get("dy")).astype(np.float64) * b.get("lu")
+    ssh0 = model.BlockInputs(bp, model.SwPar(), b.dims).f["ssh"]
+    v0, v1 = (ssh0 * area).sum(), (b.get("ssh") * area).sum()
+    assert abs(v1 - v0) <= 1e-12 * abs(v0)
+    assert not b.get("ssh")[b.get("lu") < 0.5].any()
+    assert np.abs(b.get("ssh")).max() < 0.4
 
 
 def test_blowup_flag(swlib, cuda_device):
