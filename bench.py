@@ -345,6 +345,28 @@ def main():
                "d2h_bytes_per_step": 3 * plane, "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
                "note": "per step: upload 6 prognostic arrays from pinned host memory, 1 step, download ssh/ubrtr/vbrtr"}
 
+        # For information: the analogue of an ML step where the state is resident like weights and only
+        # the per-step input (external forcing RHSx, RHSy; zero here, as in the reference) goes up and the
+        # diagnosed output (ssh) comes down.
+        frc = {n: torch.zeros(shape, dtype=torch.float64).pin_memory() for n in ("RHSx", "RHSy")}
+        def one_forcing():
+            for n in ("RHSx", "RHSy"):
+                blk.upload_ptr(n, frc[n].data_ptr())
+            m.step(1)
+            blk.download_ptr("ssh", pin["ssh"].data_ptr())
+        for _ in range(2):
+            one_forcing()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            one_forcing()
+        torch.cuda.synchronize()
+        fms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e["forcing_only_variant"] = {
+            "value": cells * world * e2e_steps / (fms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * plane,
+            "d2h_bytes_per_step": plane, "ms_per_step": fms / e2e_steps,
+            "note": "state resident; per step: upload RHSx, RHSy (external forcing), 1 step, download ssh"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, info = cpu_port_rate(S, None, 1)

@@ -373,3 +373,29 @@ def test_reference_algorithm_layer_through_envokes(swlib, cuda_device):
     fused = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=MODE_FUSED)
     with pytest.raises(Exception):
         fused.block.envoke("sw_update_ssh", 1.0)
+
+
+@pytest.mark.parametrize("tiled", [1, 0])
+def test_external_forcing_rhs(swlib, cuda_device, tiled):
+    """RHSx / RHSy (external forcing; the reference allocates them zero and never assigns them) become
+    resident on first upload and enter K7: fused and reference modes vs the oracle with the same
+    forcing, including a forcing that changes between steps."""
+    nx, ny = 97, 70
+    mask = basins.island_mask(nx, ny)
+    rng = np.random.default_rng(11)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, r_diss=5e-6), mask)
+    ms = []
+    for mode in (MODE_REFERENCE, MODE_FUSED):
+        m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, mode=mode, keep_mu=True, r_diss=5e-6)
+        if mode == MODE_FUSED:
+            m.block.set_option("tiled", tiled)
+        ms.append(m)
+    for it in range(3):
+        fx = 1e-3 * rng.standard_normal((ny, nx)); fy = 1e-3 * rng.standard_normal((ny, nx))
+        o.set("RHSx", fx); o.set("RHSy", fy)
+        o.step(7)
+        for m in ms:
+            m.block.upload("RHSx", fx); m.block.upload("RHSy", fy)
+            m.step(7)
+            for f in STATE:
+                assert np.array_equal(m.get(f), o.get(f)), (f, it, m.block.mode, tiled)
