@@ -297,6 +297,25 @@ int swcu_halo_plan(const swcu_dims *dims, int nrows, int side, int *send_row, in
  * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use. */
 int swcu_halo_exchange(swcu_ctx *ctx, int field);
 
+/* Several blocks per process (parallel.par bppnx x bppny > 1 x 1, and the reference's _GPU_MULTI_
+ * one-process-many-GPUs mode): swcu_link ties two contexts of the same process that are neighbours
+ * in a tensor-product block grid -- side, or corner; the direction follows from their dims, the
+ * contexts may live on the same device or on two devices (peer access is enabled when the topology
+ * offers it).  Linked blocks step together through swcu_step_group, which replaces the same-rank
+ * block-to-block halo copy of shared/mpp/syncborder_block2D_gen_all.fi:218-249: block arrays use
+ * global indices, so every block pulls the cells it lacks from the same (m, n) of its neighbour's
+ * array with one strided device-to-device copy per direction, ordered by events on the compute
+ * streams (no host synchronisation inside a step).  FUSED mode pulls 2 halo layers of the six
+ * prognostic arrays once per step; REFERENCE mode pulls 1 layer after every kernel whose
+ * envoke_*_sync is non-empty.  A group lists every block its members are linked to; unlinked
+ * blocks may ride along.  swcu_step on a linked context is an error (SWCU_ERR_STATE), as is mixing
+ * links with a communicator.  swcu_envoke_sync / swcu_halo_exchange on a linked context pull from
+ * the neighbours after synchronising their streams (host-blocking; the caller has issued the
+ * producing kernel on all blocks first, as the reference's loop over blocks does). */
+int swcu_link(swcu_ctx *a, swcu_ctx *b);
+int swcu_unlink(swcu_ctx *ctx); /* drops all links of ctx (swcu_destroy does this too) */
+int swcu_step_group(swcu_ctx *const *ctxs, int n, double tau, int nsteps);
+
 /* ------------------------------------------------------------------------------------------
  * Host-side input construction (C++, no GPU needed): what init_grid_data / init_ocean_data
  * (control/init_data.f90:29-125) produce for one block, in the reference layout.  These mirror

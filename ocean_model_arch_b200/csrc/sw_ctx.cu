@@ -137,6 +137,10 @@ struct swcu_ctx {
     long steps_done = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // in-process neighbours (swcu_link), by direction: S N W E SW SE NW NE
+    swcu_ctx *nbr[8] = {};
+    int nlinks = 0;
+    FusedArgs fa;  // arguments of the step in flight (FUSED)
     // per-row metric tables (FUSED): rebuilt after a metric upload, used when all arrays are row-constant
     bool metrics_dirty = true, want_tables = true, use_tables = false;
     double *tab = nullptr;
@@ -223,17 +227,6 @@ int exchange_rows(swcu_ctx *c, T *base, int nrows, cudaStream_t st)
         SWCU_NCCL(g_nccl.Send(base + (size_t)srow * c->pitch, cnt, dt, peer[side], c->comm, st));
         SWCU_NCCL(g_nccl.Recv(base + (size_t)rrow * c->pitch, cnt, dt, peer[side], c->comm, st));
     }
-    return SWCU_OK;
-}
-
-// reference-mode halo sync of a list of real(8) fields: width 1, on the compute stream
-int sync_fields(swcu_ctx *c, std::initializer_list<int> fields)
-{
-    if (!c->comm) return SWCU_OK;
-    SWCU_NCCL(g_nccl.GroupStart());
-    for (int f : fields)
-        if (int rc = exchange_rows(c, c->f8[f], 1, c->st)) { g_nccl.GroupEnd(); return rc; }
-    SWCU_NCCL(g_nccl.GroupEnd());
     return SWCU_OK;
 }
 
@@ -336,23 +329,40 @@ int envoke_kernel(swcu_ctx *c, int kid, double tau)
 }
 
 // The matching envoke_<name>_sync (sw_interface.f90:77-408, tracer_interface.f90:51-102): which fields
-// are halo-synced after the kernel (width 1, like hybrid_sync).
+// are halo-synced after the kernel (width 1, like hybrid_sync).  Returns the count, -1 for a bad id.
+int sync_list(int kid, int out[3])
+{
+    auto set = [&](std::initializer_list<int> l) { int n = 0; for (int f : l) out[n++] = f; return n; };
+    switch (kid) {
+        case SWCU_K_SW_UPDATE_SSH: return set({SWCU_F_SSHN});
+        case SWCU_K_HH_UPDATE: return set({SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N});
+        case SWCU_K_UV_TRANS_VORT: return set({SWCU_F_VORT});
+        case SWCU_K_UV_TRANS: return set({SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P});  // "lazy"
+        case SWCU_K_STRESS_COMPONENTS: return set({SWCU_F_STR_T, SWCU_F_STR_S});
+        case SWCU_K_SW_UPDATE_UV: return set({SWCU_F_VBRTRN, SWCU_F_UBRTRN});
+        case SWCU_K_HH_INIT: return set({SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH});
+        case SWCU_K_TRAN_DIFF_FLUXES: return set({SWCU_F_FLUX_X, SWCU_F_FLUX_Y});
+        case SWCU_K_TRAN_DIFF_TRACER: return set({SWCU_F_FF1N});
+        case SWCU_K_UV_DIFF2: case SWCU_K_SW_NEXT_STEP: case SWCU_K_HH_SHIFT: case SWCU_K_CHECK_SSH_ERR:
+        case SWCU_K_TRACER_NEXT_STEP: return 0;  // empty syncs in the reference
+        default: set_error("unknown kernel id %d", kid); return -1;
+    }
+}
+
+int envoke_sync_linked(swcu_ctx *c, const int *f, int n);
+
 int envoke_sync(swcu_ctx *c, int kid)
 {
-    switch (kid) {
-        case SWCU_K_SW_UPDATE_SSH: return sync_fields(c, {SWCU_F_SSHN});
-        case SWCU_K_HH_UPDATE: return sync_fields(c, {SWCU_F_HHU_N, SWCU_F_HHV_N, SWCU_F_HHH_N});
-        case SWCU_K_UV_TRANS_VORT: return sync_fields(c, {SWCU_F_VORT});
-        case SWCU_K_UV_TRANS: return sync_fields(c, {SWCU_F_HHU_P, SWCU_F_HHV_P, SWCU_F_HHH_P});  // "lazy"
-        case SWCU_K_STRESS_COMPONENTS: return sync_fields(c, {SWCU_F_STR_T, SWCU_F_STR_S});
-        case SWCU_K_SW_UPDATE_UV: return sync_fields(c, {SWCU_F_VBRTRN, SWCU_F_UBRTRN});
-        case SWCU_K_HH_INIT: return sync_fields(c, {SWCU_F_HHU, SWCU_F_HHV, SWCU_F_HHH});
-        case SWCU_K_TRAN_DIFF_FLUXES: return sync_fields(c, {SWCU_F_FLUX_X, SWCU_F_FLUX_Y});
-        case SWCU_K_TRAN_DIFF_TRACER: return sync_fields(c, {SWCU_F_FF1N});
-        case SWCU_K_UV_DIFF2: case SWCU_K_SW_NEXT_STEP: case SWCU_K_HH_SHIFT: case SWCU_K_CHECK_SSH_ERR:
-        case SWCU_K_TRACER_NEXT_STEP: return SWCU_OK;  // empty syncs in the reference
-        default: set_error("unknown kernel id %d", kid); return SWCU_ERR_ARG;
-    }
+    int f[3];
+    const int n = sync_list(kid, f);
+    if (n < 0) return SWCU_ERR_ARG;
+    if (c->nlinks && n) return envoke_sync_linked(c, f, n);
+    if (!c->comm || n == 0) return SWCU_OK;
+    SWCU_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i)
+        if (int rc = exchange_rows(c, c->f8[f[i]], 1, c->st)) { g_nccl.GroupEnd(); return rc; }
+    SWCU_NCCL(g_nccl.GroupEnd());
+    return SWCU_OK;
 }
 
 #define ENVOKE(kid) do { RC(envoke_kernel(c, kid, tau)); RC(envoke_sync(c, kid)); } while (0)
@@ -433,7 +443,8 @@ int tensor_map_for(swcu_ctx *c, const double *base, CUtensorMap *out)
     return SWCU_OK;
 }
 
-int step_fused(swcu_ctx *c, double tau)
+// The n -> n+1 update of the six prognostic arrays into the write buffers (no tracers, no swap).
+int fused_main(swcu_ctx *c, double tau)
 {
     const Geo &g = c->g;
     if (c->metrics_dirty) RC(prepare_metrics(c));
@@ -447,7 +458,7 @@ int step_fused(swcu_ctx *c, double tau)
         }
         c->alt_dirty = false;
     }
-    FusedArgs a;
+    FusedArgs &a = c->fa;
     a.ssh = c->f8[SWCU_F_SSH]; a.sshp = c->f8[SWCU_F_SSHP]; a.u = c->f8[SWCU_F_UBRTR]; a.up = c->f8[SWCU_F_UBRTRP];
     a.v = c->f8[SWCU_F_VBRTR]; a.vp = c->f8[SWCU_F_VBRTRP];
     a.ssh_o = c->alt[0]; a.sshp_o = c->alt[1]; a.u_o = c->alt[2]; a.up_o = c->alt[3]; a.v_o = c->alt[4]; a.vp_o = c->alt[5];
@@ -533,24 +544,142 @@ int step_fused(swcu_ctx *c, double tau)
         RC(rows(i0, i1, c->st));
         SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));  // strips -> exchange -> here
     }
+    return SWCU_OK;
+}
+
+// expl_tracer (control/tracer.f90:44-61) on the state fused_main just wrote (and, with a communicator,
+// just exchanged: the compute stream already waits on the exchange event)
+int fused_tracer(swcu_ctx *c)
+{
+    RC(launch_tracer(c->g, c->fa, c->g.ny_start, c->g.ny_end, c->st));
+    c->launches++;
+    if (c->comm) {
+        SWCU_NCCL(g_nccl.GroupStart());
+        int rc = exchange_rows(c, c->alt_ff[0], 2, c->st);
+        if (!rc) rc = exchange_rows(c, c->alt_ff[1], 2, c->st);
+        ncclResult_t r = g_nccl.GroupEnd();
+        if (rc) return rc;
+        if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+    }
+    return SWCU_OK;
+}
+
+// the write buffers become the current state
+void fused_swap(swcu_ctx *c)
+{
     if (c->p.use_tracers) {
-        // expl_tracer (control/tracer.f90:44-61) on the state just written (and, with a communicator,
-        // just exchanged: the compute stream already waits on the exchange event)
-        RC(launch_tracer(g, a, ns, ne, c->st));
-        c->launches++;
-        if (c->comm) {
-            SWCU_NCCL(g_nccl.GroupStart());
-            int rc = exchange_rows(c, c->alt_ff[0], 2, c->st);
-            if (!rc) rc = exchange_rows(c, c->alt_ff[1], 2, c->st);
-            ncclResult_t r = g_nccl.GroupEnd();
-            if (rc) return rc;
-            if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
-        }
         double *t = c->f8[SWCU_F_FF1]; c->f8[SWCU_F_FF1] = c->alt_ff[0]; c->alt_ff[0] = t;
         t = c->f8[SWCU_F_FF1P]; c->f8[SWCU_F_FF1P] = c->alt_ff[1]; c->alt_ff[1] = t;
     }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
+}
+
+int step_fused(swcu_ctx *c, double tau)
+{
+    RC(fused_main(c, tau));
+    if (c->p.use_tracers) RC(fused_tracer(c));
+    fused_swap(c);
     return SWCU_OK;
+}
+
+// ---- in-process neighbours (swcu_link / swcu_step_group) ---------------------------------------
+// Several blocks of one process -- on one GPU or on several -- exchange halos by pulling: block
+// arrays use global indices, so the cells a block lacks are the same (m, n) in the neighbour's
+// array and one strided device-to-device copy per direction moves them.  Replaces the same-rank
+// block-to-block copy of shared/mpp/syncborder_block2D_gen_all.fi:218-249 (and _GPU_MULTI_).
+// Directions: S N W E SW NE SE NW, so that k ^ 1 is the opposite of k.
+const int kDirX[8] = {0, 0, -1, 1, -1, 1, 1, -1};
+const int kDirY[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+
+int copy2d(void *dst, size_t dpitch, int ddev, const void *src, size_t spitch, int sdev, size_t wbytes, size_t rows,
+           cudaStream_t st)
+{
+    if (ddev == sdev) {
+        SWCU_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, wbytes, rows, cudaMemcpyDeviceToDevice, st));
+        return SWCU_OK;
+    }
+    cudaMemcpy3DPeerParms p = {};
+    p.srcDevice = sdev; p.dstDevice = ddev;
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), spitch, wbytes, rows);
+    p.dstPtr = make_cudaPitchedPtr(dst, dpitch, wbytes, rows);
+    p.extent = make_cudaExtent(wbytes, rows, 1);
+    SWCU_CUDA(cudaMemcpy3DPeerAsync(&p, st));
+    return SWCU_OK;
+}
+
+// copies the `hw` halo layers that lie towards direction k from neighbour k's interior
+template <typename T>
+int pull_halo(swcu_ctx *c, int k, T *dst, const T *src, int hw, cudaStream_t st)
+{
+    const swcu_ctx *p = c->nbr[k];
+    const swcu_dims &d = c->d;
+    int x0 = d.nx_start, x1 = d.nx_end, y0 = d.ny_start, y1 = d.ny_end;
+    if (kDirX[k] > 0) { x0 = d.nx_end + 1; x1 = d.nx_end + hw; } else if (kDirX[k] < 0) { x0 = d.nx_start - hw; x1 = d.nx_start - 1; }
+    if (kDirY[k] > 0) { y0 = d.ny_end + 1; y1 = d.ny_end + hw; } else if (kDirY[k] < 0) { y0 = d.ny_start - hw; y1 = d.ny_start - 1; }
+    T *dp = dst + (size_t)(y0 - d.bnd_y1) * c->pitch + (x0 - d.bnd_x1);
+    const T *sp = src + (size_t)(y0 - p->d.bnd_y1) * p->pitch + (x0 - p->d.bnd_x1);
+    return copy2d(dp, (size_t)c->pitch * sizeof(T), c->device, sp, (size_t)p->pitch * sizeof(T), p->device,
+                  (size_t)(x1 - x0 + 1) * sizeof(T), (size_t)(y1 - y0 + 1), st);
+}
+
+// Lockstep halo pull of `narr` arrays for a group.  Each block's compute stream waits until its
+// neighbours have produced their interiors, pulls, and then waits until its neighbours have finished
+// reading from it, so the next kernel may overwrite anything.  Nothing blocks the host.
+template <typename Get>
+int group_pull(swcu_ctx *const *cs, int n, int narr, int hw, Get get)
+{
+    if (narr == 0) return SWCU_OK;
+    for (int i = 0; i < n; ++i) {
+        if (!cs[i]->nlinks) continue;
+        Use use(cs[i]->device);
+        SWCU_CUDA(cudaEventRecord(cs[i]->ev_bnd, cs[i]->st));
+    }
+    for (int i = 0; i < n; ++i) {
+        swcu_ctx *c = cs[i];
+        if (!c->nlinks) continue;
+        Use use(c->device);
+        for (int k = 0; k < 8; ++k)
+            if (c->nbr[k]) SWCU_CUDA(cudaStreamWaitEvent(c->st, c->nbr[k]->ev_bnd, 0));
+        for (int k = 0; k < 8; ++k) {
+            if (!c->nbr[k]) continue;
+            for (int a = 0; a < narr; ++a) RC(pull_halo(c, k, get(c, a), (const double *)get(c->nbr[k], a), hw, c->st));
+        }
+        SWCU_CUDA(cudaEventRecord(c->ev_comm, c->st));
+    }
+    for (int i = 0; i < n; ++i) {
+        swcu_ctx *c = cs[i];
+        if (!c->nlinks) continue;
+        Use use(c->device);
+        for (int k = 0; k < 8; ++k)
+            if (c->nbr[k]) SWCU_CUDA(cudaStreamWaitEvent(c->st, c->nbr[k]->ev_comm, 0));
+    }
+    return SWCU_OK;
+}
+
+// Host-blocking pull for one block (per-block envoke_sync / swcu_halo_exchange on linked blocks): the
+// caller has already issued the producing kernel on every neighbour, as the reference's loop over
+// blocks does before its sync (core/kernel_interface.f90:62-86).
+template <typename T, typename Get>
+int pull_blocking(swcu_ctx *c, int hw, int narr, Get get)
+{
+    for (int k = 0; k < 8; ++k)
+        if (c->nbr[k]) { Use use(c->nbr[k]->device); SWCU_CUDA(cudaStreamSynchronize(c->nbr[k]->st)); }
+    for (int k = 0; k < 8; ++k) {
+        if (!c->nbr[k]) continue;
+        for (int a = 0; a < narr; ++a) {
+            T *dst = get(c, a);
+            const T *src = get(c->nbr[k], a);
+            if (!dst || !src) { set_error("array not resident on a linked block"); return SWCU_ERR_STATE; }
+            RC(pull_halo(c, k, dst, src, hw, c->st));
+        }
+    }
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    return SWCU_OK;
+}
+
+int envoke_sync_linked(swcu_ctx *c, const int *f, int n)
+{
+    return pull_blocking<double>(c, 1, n, [f](const swcu_ctx *x, int a) { return x->f8[f[a]]; });
 }
 
 template <typename T>
@@ -795,6 +924,7 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
 int swcu_destroy(swcu_ctx *c)
 {
     if (!c) return SWCU_OK;
+    swcu_unlink(c);
     Use use(c->device);
     cudaDeviceSynchronize();
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -897,6 +1027,7 @@ int swcu_envoke_sync(swcu_ctx *c, int kernel_id)
 int swcu_step(swcu_ctx *c, double tau, int nsteps)
 {
     if (!c || nsteps < 0) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    if (c->nlinks) { set_error("a linked block steps with its neighbours: use swcu_step_group"); return SWCU_ERR_STATE; }
     Use use(c->device);
     for (int i = 0; i < nsteps; ++i) {
         RC(c->p.mode == SWCU_MODE_FUSED ? step_fused(c, tau) : step_reference(c, tau));
@@ -910,6 +1041,7 @@ int swcu_profile_steps(swcu_ctx *c, double tau, int nsteps,
 {
     if (!c || nsteps < 0 || !prep_ms || !prep_launches || !update_ms || !update_launches) { set_error("bad argument"); return SWCU_ERR_ARG; }
     if (c->p.mode != SWCU_MODE_FUSED) { set_error("profile_steps needs FUSED mode"); return SWCU_ERR_STATE; }
+    if (c->nlinks) { set_error("profile_steps on a linked block"); return SWCU_ERR_STATE; }
     Use use(c->device);
     c->prof = true;
     int rc = SWCU_OK;
@@ -1000,6 +1132,7 @@ int swcu_comm_init(swcu_ctx *c, int nranks, int rank, const void *id128)
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return SWCU_ERR_ARG; }
     if (c->comm) { set_error("communicator already attached"); return SWCU_ERR_STATE; }
     if (nranks == 1) return SWCU_OK;
+    if (c->nlinks) { set_error("a block has either in-process links or a communicator"); return SWCU_ERR_STATE; }
     RC(nccl_load());
     Use use(c->device);
     ncclUniqueId id;
@@ -1019,6 +1152,115 @@ int swcu_comm_destroy(swcu_ctx *c)
     return SWCU_OK;
 }
 
+int swcu_link(swcu_ctx *a, swcu_ctx *b)
+{
+    if (!a || !b || a == b) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    if (a->comm || b->comm) { set_error("a block has either in-process links or a communicator"); return SWCU_ERR_STATE; }
+    if (memcmp(&a->p, &b->p, sizeof(swcu_params)) != 0) { set_error("linked blocks need identical parameters"); return SWCU_ERR_ARG; }
+    auto rel = [](int a0, int a1, int b0, int b1, int *out) {
+        if (b0 == a1 + 1) { *out = 1; return true; }
+        if (b1 + 1 == a0) { *out = -1; return true; }
+        if (b0 == a0 && b1 == a1) { *out = 0; return true; }
+        return false;
+    };
+    int dx = 0, dy = 0;
+    if (!rel(a->d.nx_start, a->d.nx_end, b->d.nx_start, b->d.nx_end, &dx) ||
+        !rel(a->d.ny_start, a->d.ny_end, b->d.ny_start, b->d.ny_end, &dy) || (dx == 0 && dy == 0)) {
+        set_error("blocks [%d:%d]x[%d:%d] and [%d:%d]x[%d:%d] are not neighbours of one block grid", a->d.nx_start,
+                  a->d.nx_end, a->d.ny_start, a->d.ny_end, b->d.nx_start, b->d.nx_end, b->d.ny_start, b->d.ny_end);
+        return SWCU_ERR_ARG;
+    }
+    for (const swcu_ctx *c : {a, b})
+        if (c->d.nx_end - c->d.nx_start + 1 < 2 || c->d.ny_end - c->d.ny_start + 1 < 2) {
+            set_error("a linked block needs at least 2 x 2 interior cells (halo width 2)");
+            return SWCU_ERR_ARG;
+        }
+    int k = -1;
+    for (int i = 0; i < 8; ++i) if (kDirX[i] == dx && kDirY[i] == dy) k = i;
+    if (a->nbr[k] || b->nbr[k ^ 1]) { set_error("that side is already linked"); return SWCU_ERR_STATE; }
+    if (a->device != b->device) {  // direct peer copies where the topology allows; staged otherwise
+        for (int pass = 0; pass < 2; ++pass) {
+            const int from = pass ? b->device : a->device, to = pass ? a->device : b->device;
+            int can = 0;
+            SWCU_CUDA(cudaDeviceCanAccessPeer(&can, from, to));
+            if (!can) continue;
+            Use use(from);
+            cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+    }
+    a->nbr[k] = b; b->nbr[k ^ 1] = a;
+    a->nlinks++; b->nlinks++;
+    return SWCU_OK;
+}
+
+int swcu_unlink(swcu_ctx *c)
+{
+    if (!c) return SWCU_OK;
+    for (int k = 0; k < 8; ++k) {
+        swcu_ctx *p = c->nbr[k];
+        if (!p) continue;
+        { Use use(p->device); cudaStreamSynchronize(p->st); }
+        p->nbr[k ^ 1] = nullptr; p->nlinks--;
+        c->nbr[k] = nullptr; c->nlinks--;
+    }
+    return SWCU_OK;
+}
+
+int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
+{
+    if (!cs || n < 1 || nsteps < 0) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    for (int i = 0; i < n; ++i) {
+        if (!cs[i]) { set_error("null block in the group"); return SWCU_ERR_ARG; }
+        if (cs[i]->comm) { set_error("a block with a communicator steps with swcu_step"); return SWCU_ERR_STATE; }
+        if (memcmp(&cs[i]->p, &cs[0]->p, sizeof(swcu_params)) != 0) { set_error("blocks of a group need identical parameters"); return SWCU_ERR_ARG; }
+        for (int j = 0; j < i; ++j) if (cs[j] == cs[i]) { set_error("block listed twice"); return SWCU_ERR_ARG; }
+        for (int k = 0; k < 8; ++k) {
+            if (!cs[i]->nbr[k]) continue;
+            bool found = false;
+            for (int j = 0; j < n; ++j) found = found || cs[j] == cs[i]->nbr[k];
+            if (!found) { set_error("block %d is linked to a block outside the group", i); return SWCU_ERR_ARG; }
+        }
+    }
+    const swcu_params &p = cs[0]->p;
+    // one (kernel, sync) pair of the reference's algorithm layer over all blocks of the group
+    auto envoke = [&](int kid) -> int {
+        for (int i = 0; i < n; ++i) { Use use(cs[i]->device); RC(envoke_kernel(cs[i], kid, tau)); }
+        int f[3];
+        const int nf = sync_list(kid, f);
+        if (nf < 0) return SWCU_ERR_ARG;
+        return group_pull(cs, n, nf, 1, [&f](const swcu_ctx *x, int a) { return x->f8[f[a]]; });
+    };
+    for (int s = 0; s < nsteps; ++s) {
+        if (p.mode == SWCU_MODE_FUSED) {
+            for (int i = 0; i < n; ++i) { Use use(cs[i]->device); RC(fused_main(cs[i], tau)); }
+            RC(group_pull(cs, n, 6, 2, [](const swcu_ctx *x, int a) { return x->alt[a]; }));
+            if (p.use_tracers) {
+                for (int i = 0; i < n; ++i) { Use use(cs[i]->device); RC(fused_tracer(cs[i])); }
+                RC(group_pull(cs, n, 2, 2, [](const swcu_ctx *x, int a) { return x->alt_ff[a]; }));
+            }
+            for (int i = 0; i < n; ++i) fused_swap(cs[i]);
+        } else {  // control/shallow_water/shallow_water.f90:22-94, then control/tracer.f90:44-61
+            RC(envoke(SWCU_K_SW_UPDATE_SSH));
+            if (p.full_free_surface > 0) RC(envoke(SWCU_K_HH_UPDATE));
+            if (p.trans_terms > 0) { RC(envoke(SWCU_K_UV_TRANS_VORT)); RC(envoke(SWCU_K_UV_TRANS)); }
+            if (p.ksw_lat > 0) { RC(envoke(SWCU_K_STRESS_COMPONENTS)); RC(envoke(SWCU_K_UV_DIFF2)); }
+            RC(envoke(SWCU_K_SW_UPDATE_UV));
+            RC(envoke(SWCU_K_SW_NEXT_STEP));
+            if (p.full_free_surface > 0) { RC(envoke(SWCU_K_HH_SHIFT)); RC(envoke(SWCU_K_HH_INIT)); }
+            RC(envoke(SWCU_K_CHECK_SSH_ERR));
+            if (p.use_tracers > 0) {
+                RC(envoke(SWCU_K_TRAN_DIFF_FLUXES));
+                RC(envoke(SWCU_K_TRAN_DIFF_TRACER));
+                RC(envoke(SWCU_K_TRACER_NEXT_STEP));
+            }
+        }
+        for (int i = 0; i < n; ++i) cs[i]->steps_done++;
+    }
+    return SWCU_OK;
+}
+
 int swcu_halo_plan(const swcu_dims *d, int nrows, int side, int *send_row, int *recv_row)
 {
     if (!d || !send_row || !recv_row || nrows < 1 || nrows > 2 || (side != 0 && side != 1)) {
@@ -1035,6 +1277,17 @@ int swcu_halo_plan(const swcu_dims *d, int nrows, int side, int *send_row, int *
 int swcu_halo_exchange(swcu_ctx *c, int field)
 {
     if (!c) return SWCU_ERR_ARG;
+    if (c->nlinks) {
+        Use use(c->device);
+        const int hw = c->p.mode == SWCU_MODE_FUSED ? 2 : 1;
+        if (is_f8(field)) {
+            if (c->p.mode == SWCU_MODE_FUSED && state_slot(field) >= 0) c->alt_dirty = true;
+            return pull_blocking<double>(c, hw, 1, [field](const swcu_ctx *x, int) { return x->f8[field]; });
+        }
+        if (is_f4(field)) return pull_blocking<float>(c, hw, 1, [field](const swcu_ctx *x, int) { return x->f4[field - 100]; });
+        set_error("unknown field id %d", field);
+        return SWCU_ERR_ARG;
+    }
     if (!c->comm) return SWCU_OK;
     Use use(c->device);
     const bool fused = c->p.mode == SWCU_MODE_FUSED;

