@@ -10,8 +10,10 @@
 !                                         download_ssh_cuda, finalize_device_data_cuda, and the
 !                                         14 envoke_<name>_kernel_cuda / _sync_cuda pairs
 !
-! One MPI rank drives one GPU and owns one block (parallel.par: bppnx = 1, bppny = 1 per rank on a
-! 1 x nranks process grid, i.e. y-slabs).  Halo exchange happens inside swcu_step over NCCL.
+! Across MPI ranks the cut is y-slabs (1 x nranks process grid), one block per rank; the halo
+! exchange then happens inside swcu_step over NCCL.  A single rank may instead own any
+! bppnx x bppny blocks (dealt over the visible GPUs): they are linked pairwise and step together
+! through swcu_step_group, which pulls halos device-to-device.
 !-----------------------------------------------------------------------------------------------
 module swcuda_c_binding
     use iso_c_binding
@@ -113,6 +115,23 @@ module swcuda_c_binding
             integer(c_int), value :: nsteps
             integer(c_int) :: rc
         end function
+        function swcu_link(a, b) bind(C, name="swcu_link") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: a, b
+            integer(c_int) :: rc
+        end function
+        function swcu_step_group(ctxs, n, tau, nsteps) bind(C, name="swcu_step_group") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), intent(in) :: ctxs(*)
+            integer(c_int), value :: n
+            real(c_double), value :: tau
+            integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function swcu_device_count() bind(C, name="swcu_device_count") result(n)
+            import :: c_int
+            integer(c_int) :: n
+        end function
         function swcu_synchronize(ctx, bad_cells) bind(C, name="swcu_synchronize") result(rc)
             import :: c_ptr, c_int, c_long
             type(c_ptr), value :: ctx
@@ -151,7 +170,7 @@ module shallow_water_interface_cuda_module
     use decomposition_module, only: domain_type, domain => domain_data
     use ocean_module, only: ocean_type, ocean_data
     use grid_module, only: grid_type, grid_data
-    use config_sw_module, only: full_free_surface, time_smooth, trans_terms, ksw_lat, use_tracers
+    use config_sw_module, only: full_free_surface, time_smooth, trans_terms, ksw_lat, use_tracers, tracer_num
     use errors_module, only: abort_model
     use kernel_interface_module, only: kernel_parameters_type
     use mpp_sync_module, only: sync_parameters_type
@@ -199,24 +218,42 @@ contains
         call check(swcu_upload(ctx(k), field, c_loc(a)), 'upload')
     end subroutine
 
+    ! .true. if local blocks k1 and k2 are side or corner neighbours in the block grid
+    logical function blocks_touch(k1, k2)
+        integer, intent(in) :: k1, k2
+        integer :: dx, dy
+        dx = rel(domain%bnx_start(k1), domain%bnx_end(k1), domain%bnx_start(k2), domain%bnx_end(k2))
+        dy = rel(domain%bny_start(k1), domain%bny_end(k1), domain%bny_start(k2), domain%bny_end(k2))
+        blocks_touch = dx /= 2 .and. dy /= 2 .and. (dx /= 0 .or. dy /= 0)
+    contains
+        integer function rel(a0, a1, b0, b1)   ! +1 / -1 adjacent, 0 same range, 2 unrelated
+            integer, intent(in) :: a0, a1, b0, b1
+            rel = 2
+            if (b0 == a1 + 1) rel = 1
+            if (b1 + 1 == a0) rel = -1
+            if (b0 == a0 .and. b1 == a1) rel = 0
+        end function
+    end function
+
     ! replaces init_device_data (control/init_data.f90:127-145): called once after init_grid_data /
     ! init_ocean_data have filled the host arrays
     subroutine init_device_data_cuda()
         type(swcu_dims) :: d
         type(swcu_params) :: p
         character(kind=c_char) :: id(128)
-        integer :: k, ierr
+        integer :: k, k2, ierr, ndev
 
+        ndev = max(1, int(swcu_device_count()))
+        if (mpp_count > 1 .and. domain%bcount > 1) call abort_model('swcuda: several ranks need one block per rank')
         allocate(ctx(domain%bcount))
         p%full_free_surface = full_free_surface; p%trans_terms = trans_terms; p%ksw_lat = ksw_lat
         p%time_smooth = time_smooth; p%use_tracers = use_tracers; p%mode = SWCU_MODE_FUSED
-        if (use_tracers > 0) p%mode = SWCU_MODE_REFERENCE
         do k = 1, domain%bcount
             d%nx_start = domain%bnx_start(k); d%nx_end = domain%bnx_end(k)
             d%ny_start = domain%bny_start(k); d%ny_end = domain%bny_end(k)
             d%bnd_x1 = domain%bbnd_x1(k); d%bnd_x2 = domain%bbnd_x2(k)
             d%bnd_y1 = domain%bbnd_y1(k); d%bnd_y2 = domain%bbnd_y2(k)
-            call check(swcu_create(ctx(k), d, p, int(k - 1, c_int)), 'create')
+            call check(swcu_create(ctx(k), d, p, int(mod(k - 1, ndev), c_int)), 'create')
             call up4(k, SWCU_F_LU,  grid_data%lu %block(k)%field); call up4(k, SWCU_F_LUU, grid_data%luu%block(k)%field)
             call up4(k, SWCU_F_LUH, grid_data%luh%block(k)%field); call up4(k, SWCU_F_LCU, grid_data%lcu%block(k)%field)
             call up4(k, SWCU_F_LCV, grid_data%lcv%block(k)%field); call up4(k, SWCU_F_LLU, grid_data%llu%block(k)%field)
@@ -231,7 +268,18 @@ contains
             call up8(k, SWCU_F_UBRTR,  ocean_data%ubrtr %block(k)%field); call up8(k, SWCU_F_UBRTRP, ocean_data%ubrtrp%block(k)%field)
             call up8(k, SWCU_F_VBRTR,  ocean_data%vbrtr %block(k)%field); call up8(k, SWCU_F_VBRTRP, ocean_data%vbrtrp%block(k)%field)
             call up8(k, SWCU_F_MU,     ocean_data%mu    %block(k)%field)
+            if (use_tracers > 0) then   ! expl_tracer runs inside the step (control/tracer.f90:44-61)
+                if (tracer_num /= 1) call abort_model('swcuda: the device step carries one tracer (tracer_num = 1)')
+                call up8(k, SWCU_F_FF1,  ocean_data%ff1(1) %block(k)%field)
+                call up8(k, SWCU_F_FF1P, ocean_data%ff1p(1)%block(k)%field)
+            endif
             call check(swcu_envoke_hh_init(ctx(k)), 'hh_init')
+        enddo
+        ! several blocks in this rank: link every pair of side / corner neighbours once
+        do k = 1, domain%bcount
+            do k2 = k + 1, domain%bcount
+                if (blocks_touch(k, k2)) call check(swcu_link(ctx(k), ctx(k2)), 'link')
+            enddo
         enddo
         ! one NCCL communicator over the y-slab ranks; the id travels over the existing MPI communicator
         if (mpp_count > 1) then
@@ -245,11 +293,12 @@ contains
     ! calls it from inside the long-lived !$omp parallel region, so only the master thread launches
     subroutine expl_shallow_water_cuda(tau)
         real(wp8), intent(in) :: tau
-        integer :: k
         !$omp master
-        do k = 1, domain%bcount
-            call check(swcu_step(ctx(k), real(tau, c_double), 1_c_int), 'step')
-        enddo
+        if (domain%bcount > 1) then
+            call check(swcu_step_group(ctx, int(domain%bcount, c_int), real(tau, c_double), 1_c_int), 'step_group')
+        else
+            call check(swcu_step(ctx(1), real(tau, c_double), 1_c_int), 'step')
+        endif
         !$omp end master
         !$omp barrier
     end subroutine
