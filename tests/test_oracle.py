@@ -147,3 +147,53 @@ def test_linear_gravity_mode_known_answer():
     assert np.abs(got - want).max() < 1e-9 * abs(want) + 1e-11, (got.min(), got.max(), want)
     assert 0.05 < np.abs(a).max() < 0.1 * 1.001                  # neutral: no growth (the start excites a tiny computational mode)
     assert np.sign(a).min() < 0 < np.sign(a).max()               # it really oscillates
+
+
+# ---- the C oracle against an independent NumPy restatement written from the Fortran sources -------------
+import np_restatement as npr  # noqa: E402
+
+
+def _numpy_twin(o, cfg, rng=None):
+    """NumpyModel holding a copy of every array of the (single-block) oracle model."""
+    fields = {n: o.get(n) for n in npr.F8 + npr.F4}
+    if cfg.use_tracers:
+        fields.update({n: o.get(n) for n in npr.F8_TRACER})
+    return npr.NumpyModel(fields, full_free_surface=cfg.full_free_surface, trans_terms=cfg.trans_terms,
+                          ksw_lat=cfg.ksw_lat, time_smooth=cfg.time_smooth, use_tracers=cfg.use_tracers)
+
+
+@pytest.mark.parametrize("variant", ["shipped", "viscous_friction_tracer", "rigid_lid", "no_adv_no_visc", "cartesian",
+                                     "rough_bottom_forced"])
+def test_c_oracle_equals_numpy_restatement_bitwise(variant):
+    nx, ny = 61, 47
+    kw = dict(shipped={}, viscous_friction_tracer=dict(keep_mu=1, r_diss=5e-6, use_tracers=1),
+              rigid_lid=dict(full_free_surface=0, keep_mu=1), no_adv_no_visc=dict(trans_terms=0, ksw_lat=0),
+              cartesian=dict(curve_grid=0, keep_mu=1, use_tracers=1, time_step=0.75),
+              rough_bottom_forced=dict(keep_mu=1, r_diss=1e-5, use_tracers=1))[variant]
+    cfg = make_config(nx, ny, **kw)
+    o = OracleModel(cfg, basins.island_mask(nx, ny))
+    if variant == "rough_bottom_forced":
+        # random bathymetry, viscosity and external forcing (arrays the shipped set-up leaves constant / zero)
+        rng = np.random.default_rng(11)
+        o.set("hhq_rest", 50.0 + 100.0 * rng.random((ny, nx)))
+        o.set("mu", 2000.0 * rng.random((ny, nx)))
+        o.set("RHSx", 1e-2 * rng.standard_normal((ny, nx)))
+        o.set("RHSy", 1e-2 * rng.standard_normal((ny, nx)))
+        o.set("ubrtr", 0.1 * rng.standard_normal((ny, nx)) * o.get("lcu"))
+        o.set("ubrtrp", o.get("ubrtr"))
+        o.set("vbrtr", 0.1 * rng.standard_normal((ny, nx)) * o.get("lcv"))
+        o.set("vbrtrp", o.get("vbrtr"))
+        o.step(1)   # lets the oracle's own hh_init pick the new bathymetry up before the twin is taken
+    twin = _numpy_twin(o, cfg)
+    tau = float(np.float32(cfg.time_step))
+    names = list(npr.F8) + (list(npr.F8_TRACER) if cfg.use_tracers else [])
+    done = 0
+    for upto in (1, 2, 25):
+        o.step(upto - done); twin.step(tau, upto - done)
+        done = upto
+        for n in names:
+            assert np.array_equal(twin.f[n], o.get(n), equal_nan=True), (variant, n, upto)
+    assert twin.bad == 0
+    assert np.abs(o.get("ssh")).max() > 1e-3          # the comparison is not of zeros
+    if cfg.use_tracers:
+        assert np.abs(o.get("ff1")).max() > 1e-3
