@@ -197,3 +197,79 @@ def test_c_oracle_equals_numpy_restatement_bitwise(variant):
     assert np.abs(o.get("ssh")).max() > 1e-3          # the comparison is not of zeros
     if cfg.use_tracers:
         assert np.abs(o.get("ff1")).max() > 1e-3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c_kernels_equal_numpy_kernels_on_random_fields_and_masks(seed):
+    """Per kernel, with every mask an INDEPENDENT random 0/1 field (so masked stores, the slu divisors and
+    every stencil arm are exercised in combinations a real coastline never produces) and random positive
+    metrics that vary in both directions."""
+    rng = np.random.default_rng(seed)
+    nx, ny = 37, 29
+    b = npr.Block(nx, ny)
+    dims = (3, nx - 2, 3, ny - 2, 1, nx, 1, ny)
+    M = {n: (rng.random((ny, nx)) < 0.7).astype(np.float32) for n in ("lu", "luu", "luh", "lcu", "lcv", "llu", "llv")}
+    G = {n: (1000.0 + 500.0 * rng.random((ny, nx))).astype(np.float32)
+         for n in ("dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb")}
+    G["rlh_s"] = (1e-4 * rng.standard_normal((ny, nx))).astype(np.float32)
+    G["r_diss"] = (1e-5 * rng.random((ny, nx))).astype(np.float32)
+
+    def fld(scale=1.0, positive=False):
+        a = rng.random((ny, nx)) + 0.5 if positive else rng.standard_normal((ny, nx))
+        return np.ascontiguousarray(scale * a)
+    metrics8 = [G[n] for n in ("dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb")]
+    tau, ts = 0.75, 0.5
+
+    def both(cname, c_args, np_fn, np_args, outs):
+        """outs: indices (into c_args, np_args) of the arrays the kernel writes."""
+        ca = [a.copy() if isinstance(a, np.ndarray) else a for a in c_args]
+        na = [a.copy() if isinstance(a, np.ndarray) else a for a in np_args]
+        call_kernel(cname, dims, *ca)
+        np_fn(b, *na)
+        for ic, inp in outs:
+            assert np.array_equal(ca[ic], na[inp], equal_nan=True), (cname, ic)
+            assert not np.array_equal(ca[ic], c_args[ic]), (cname, ic, "kernel wrote nothing")
+
+    u, v, up, vp, ssh, sshp = fld(0.3), fld(0.3), fld(0.3), fld(0.3), fld(0.5), fld(0.5)
+    un, vn, sshn = fld(0.3), fld(0.3), fld(0.5)
+    hq, hu, hv, hh = (fld(100.0, True) for _ in range(4))
+    dep = [fld(100.0, True) for _ in range(12)]
+    h_r, mu, vort, st, ss = fld(100.0, True), fld(1000.0, True), fld(1e-3), fld(1e-4), fld(1e-4)
+    rx, ry, rxa, rya, rxd, ryd = (fld(1e-2) for _ in range(6))
+    ff, ffp, ffn, fx, fy = fld(1.0), fld(1.0), fld(1.0), fld(1.0), fld(1.0)
+    lu, luu, luh, lcu, lcv, llu, llv = (M[n] for n in ("lu", "luu", "luh", "lcu", "lcv", "llu", "llv"))
+
+    a = [tau, lu, G["dx"], G["dy"], G["dxh"], G["dyh"], hu, hv, sshn, sshp, u, v]
+    both("sw_update_ssh_kernel", a, npr.sw_update_ssh, a, [(8, 8)])
+    a = [lu, llu, llv, luh, *metrics8, dep[2], dep[5], dep[8], dep[11], ssh, h_r]
+    both("hh_update_kernel", a, npr.hh_update, a, [(12, 12), (13, 13), (14, 14), (15, 15)])
+    a = [luu, G["dxt"], G["dyt"], G["dxb"], G["dyb"], u, v, vort]
+    both("uv_trans_vort_kernel", a, npr.uv_trans_vort, a, [(7, 7)])
+    c = [lcu, lcv, luu, G["dxh"], G["dyh"], u, v, vort, hq, hu, hv, hh, rxa, rya]
+    n = [lcu, lcv, luu, G["dxh"], G["dyh"], u, v, vort, hu, hv, hh, rxa, rya]
+    both("uv_trans_kernel", c, npr.uv_trans, n, [(12, 11), (13, 12)])
+    a = [lu, luu, *metrics8, up, vp, st, ss]
+    both("stress_components_kernel", a, npr.stress_components, a, [(12, 12), (13, 13)])
+    c = [lcu, lcv, *metrics8, mu, st, ss, hq, hu, hv, hh, rxd, ryd]
+    n = [lcu, lcv, *metrics8, mu, st, ss, hq, hh, rxd, ryd]
+    both("uv_diff2_kernel", c, npr.uv_diff2, n, [(17, 15), (18, 16)])
+    a = [tau, lcu, lcv, G["dxt"], G["dyt"], G["dxh"], G["dyh"], G["dxb"], G["dyb"], dep[3], dep[5], dep[4], dep[6], dep[8],
+         dep[7], hh, ssh, u, un, up, v, vn, vp, G["r_diss"], G["rlh_s"], rx, ry, rxa, rya, rxd, ryd]
+    both("sw_update_uv", a, npr.sw_update_uv, a, [(18, 18), (21, 21)])
+    a = [ts, lu, lcu, lcv, ssh, sshn, sshp, u, un, up, v, vn, vp]
+    both("sw_next_step", a, npr.sw_next_step, a, [(4, 4), (6, 6), (7, 7), (9, 9), (10, 10), (12, 12)])
+    a = [ts, lu, llu, llv, luh, *dep]
+    both("hh_shift_kernel", a, npr.hh_shift, a, [(5 + i, 5 + i) for i in (0, 1, 3, 4, 6, 7, 9, 10)])
+    a = [1, lu, llu, llv, luh, *metrics8, *dep, ssh, sshp, h_r]
+    both("hh_init_kernel", a, npr.hh_init, a, [(13 + i, 13 + i) for i in range(12)])
+    c = [lcu, lcv, G["dxt"], G["dyt"], G["dxh"], G["dyh"], hu, hv, ff, ffp, u, v, mu, 1.0, fx, fy]
+    n = [lcu, lcv, G["dxt"], G["dyt"], G["dxh"], G["dyh"], hu, hv, ff, u, v, mu, 1.0, fx, fy]
+    both("tran_diff_fluxes_kernel", c, npr.tran_diff_fluxes, n, [(14, 13), (15, 14)])
+    a = [lu, G["dx"], G["dy"], tau, dep[2], dep[1], fx, fy, ffp, ffn]
+    both("tran_diff_tracer_kernel", a, npr.tran_diff_tracer, a, [(9, 9)])
+    a = [ts, lu, ffn, ffp, ff]
+    both("tracer_next_step_kernel", a, npr.tracer_next_step, a, [(3, 3), (4, 4)])
+    bad = ssh.copy()
+    bad[5, 7], bad[9, 9], bad[11, 4] = 2e4, np.nan, -1e4
+    want = int(sum(lu[j, i] > 0.5 for j, i in ((5, 7), (9, 9), (11, 4))))
+    assert call_kernel("check_ssh_err_kernel", dims, lu, bad) == npr.check_ssh_err(b, lu, bad) == want
