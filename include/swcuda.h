@@ -341,6 +341,26 @@ int swh_gaussian(const swcu_dims *d, const float *lu, double *ssh, double sigma,
  * `i` of `nb` along an axis of `ncells` computational cells. */
 int swh_uniform_split(int ncells, int nb, int i, int *start, int *size);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-side construction of a resident context's static inputs: init_grid_data
+ * (control/init_data.f90:96-125) without building and uploading sixteen 2-D arrays.
+ * swcu_init_grid fills the seven masks and the nine metric / Coriolis arrays of the context:
+ *   - lu from `mask` (the GLOBAL nx*ny integer mask in the layout of swh_masks, only the block's
+ *     window is copied to the device; NULL = "none", the rectangular basin of tools/io.f90:49-59) and
+ *     the derived masks with the reference's tests (kernel/service/grid_kernels.f90:18-92), on the device;
+ *   - dx .. dyb, rlh_s: where they are constant along x (carthesian, or spherical with
+ *     rotation_on_lat = 0) one column is evaluated on the host by swh_metrics -- same libm calls,
+ *     same real(4) roundings -- and spread over the rows on the device; with a rotated pole the arrays
+ *     are built on the host and uploaded, as swh_metrics + swcu_upload would.
+ * Results equal swh_masks / swh_metrics + swcu_upload bit for bit.
+ * swcu_fill / swcu_copy_field are data2D%fill and %copy_from on the resident arrays (whole block
+ * array incl. frame, core/data_types.f90:665-716): hhq_rest = 100, mu = 0, sshp = ssh ...
+ * (control/init_data.f90:57-58,76-77,112-114).  Fields FUSED mode does not keep are accepted and
+ * ignored, like swcu_upload does. */
+int swcu_init_grid(swcu_ctx *ctx, const swh_basin *basin, const int *mask);
+int swcu_fill(swcu_ctx *ctx, int field, double value);
+int swcu_copy_field(swcu_ctx *ctx, int dst_field, int src_field);
+
 #ifdef __cplusplus
 }
 #endif

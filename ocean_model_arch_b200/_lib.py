@@ -103,6 +103,9 @@ _SIGNATURES = {
     "swcu_comm_destroy": [_P],
     "swcu_halo_plan": [_DIMS, _I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swcu_halo_exchange": [_P, _I],
+    "swcu_init_grid": [_P, _P, _P],
+    "swcu_fill": [_P, _I, _D],
+    "swcu_copy_field": [_P, _I, _I],
     "swcu_link": [_P, _P],
     "swcu_unlink": [_P],
     "swcu_step_group": [C.POINTER(_P), _I, _D, _I],

@@ -1261,6 +1261,146 @@ int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
     return SWCU_OK;
 }
 
+int swcu_init_grid(swcu_ctx *c, const swh_basin *b, const int *mask)
+{
+    if (!c || !b) { set_error("null argument"); return SWCU_ERR_ARG; }
+    const swcu_dims &d = c->d;
+    if (d.bnd_x1 < 1 || d.bnd_x2 > b->nx || d.bnd_y1 < 1 || d.bnd_y2 > b->ny) {
+        set_error("block array [%d:%d]x[%d:%d] leaves the %d x %d basin", d.bnd_x1, d.bnd_x2, d.bnd_y1, d.bnd_y2, b->nx, b->ny);
+        return SWCU_ERR_ARG;
+    }
+    if (b->curve_grid != 0 && b->curve_grid != 1) { set_error("curve_grid must be 0 or 1"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    const int w = c->w, h = c->h;
+    int rc = SWCU_OK;
+    std::vector<void *> scratch;
+    auto tmp = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (rc) return p;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "scratch for swcu_init_grid"); return nullptr; }
+        scratch.push_back(p);
+        return p;
+    };
+    // ---- masks
+    int *land = nullptr;
+    if (mask) {
+        land = (int *)tmp((size_t)w * h * sizeof(int));
+        if (!rc) {
+            cudaError_t e = cudaMemcpy2DAsync(land, (size_t)w * sizeof(int),
+                                              mask + (size_t)(d.bnd_y1 - 1) * b->nx + (d.bnd_x1 - 1), (size_t)b->nx * sizeof(int),
+                                              (size_t)w * sizeof(int), (size_t)h, cudaMemcpyHostToDevice, c->st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "mask window upload");
+        }
+    }
+    unsigned char *lu = (unsigned char *)tmp((size_t)w * h);
+    if (!rc) rc = launch_init_lu(c->g, w, h, b->nx, b->ny, land, lu, c->st);
+    if (!rc) {
+        if (fused) rc = launch_init_masks(c->g, w, h, lu, c->mask, nullptr, c->st);
+        else {
+            float *const f[7] = {F4(c, SWCU_F_LU), F4(c, SWCU_F_LUU), F4(c, SWCU_F_LUH), F4(c, SWCU_F_LCU),
+                                 F4(c, SWCU_F_LCV), F4(c, SWCU_F_LLU), F4(c, SWCU_F_LLV)};
+            rc = launch_init_masks(c->g, w, h, lu, nullptr, f, c->st);
+        }
+        c->masks_dirty = true;
+        c->launches += 2;
+    }
+    // ---- metrics and Coriolis parameter
+    const int ids[9] = {SWCU_F_DX, SWCU_F_DY, SWCU_F_DXT, SWCU_F_DYT, SWCU_F_DXH, SWCU_F_DYH, SWCU_F_DXB, SWCU_F_DYB, SWCU_F_RLH_S};
+    const bool row_constant = b->curve_grid == 0 || b->rotation_on_lat == 0.0;
+    if (!rc && row_constant) {
+        // one array column outside [2..nx-1] (m = 1) and one inside (m = 2), evaluated by swh_metrics itself
+        const swcu_dims strip = {2, 2, d.ny_start, d.ny_end, 1, 2, d.bnd_y1, d.bnd_y2};
+        std::vector<float> col[9];
+        float *ptr[9];
+        for (int k = 0; k < 9; ++k) { col[k].assign((size_t)2 * h, 0.0f); ptr[k] = col[k].data(); }
+        rc = swh_metrics(b, &strip, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], ptr[6], ptr[7], ptr[8]);
+        if (rc) set_error("swh_metrics rejected the basin");
+        std::vector<float> prof((size_t)9 * 2 * h);
+        for (int k = 0; k < 9; ++k)
+            for (int side = 0; side < 2; ++side)
+                for (int j = 0; j < h; ++j) prof[((size_t)k * 2 + side) * h + j] = col[k][(size_t)j * 2 + side];
+        float *prof_dev = (float *)tmp(prof.size() * sizeof(float));
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(prof_dev, prof.data(), prof.size() * sizeof(float), cudaMemcpyHostToDevice, c->st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "metric profile upload");
+        }
+        if (!rc) {
+            float *dst[9];
+            for (int k = 0; k < 9; ++k) dst[k] = F4(c, ids[k]);
+            rc = launch_expand_rows(c->g, w, h, b->nx, dst, prof_dev, c->st);
+            c->launches++;
+        }
+        if (!rc) {   // the profile vector must outlive the asynchronous copy
+            cudaError_t e = cudaStreamSynchronize(c->st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "swcu_init_grid");
+        }
+    } else if (!rc) {
+        // rotated pole: rlh_s varies along x; build the 2-D arrays on the host like the reference and upload them
+        std::vector<float> arr[9];
+        float *ptr[9];
+        for (int k = 0; k < 9; ++k) { arr[k].assign((size_t)w * h, 0.0f); ptr[k] = arr[k].data(); }
+        rc = swh_metrics(b, &d, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], ptr[5], ptr[6], ptr[7], ptr[8]);
+        for (int k = 0; k < 9 && !rc; ++k) rc = upload_impl(c, ids[k], ptr[k], false);
+        if (!rc) {
+            cudaError_t e = cudaStreamSynchronize(c->st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "swcu_init_grid");
+        }
+    }
+    c->metrics_dirty = true;
+    cudaStreamSynchronize(c->st);
+    for (void *p : scratch) cudaFree(p);
+    return rc;
+}
+
+int swcu_fill(swcu_ctx *c, int field, double value)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    if (is_f8(field)) {
+        if (is_tracer_field(field) && !c->p.use_tracers) { set_error("tracer field without use_tracers"); return SWCU_ERR_STATE; }
+        if (fused && (field == SWCU_F_RHSX || field == SWCU_F_RHSY) && !c->has_rhs) {
+            c->has_rhs = true;
+            RC(alloc8(c, SWCU_F_RHSX)); RC(alloc8(c, SWCU_F_RHSY));
+        }
+        if (fused && !fused_keeps8(c, field) && !(c->p.use_tracers && (field == SWCU_F_FF1 || field == SWCU_F_FF1P)))
+            return SWCU_OK;  // derived or n+1 array: recomputed on the device
+        RC(launch_fill8(c->w, c->h, c->pitch, c->f8[field], value, c->st));
+        if (fused && (state_slot(field) >= 0 || is_tracer_field(field))) c->alt_dirty = true;
+        c->launches++;
+        return SWCU_OK;
+    }
+    if (is_f4(field)) {
+        if (mask_bit(field)) { set_error("masks are set by swcu_init_grid or swcu_upload"); return SWCU_ERR_ARG; }
+        if (fused && field == SWCU_F_R_DISS && !c->has_rdiss) { c->has_rdiss = true; RC(alloc4(c, SWCU_F_R_DISS)); }
+        if (fused && !fused_keeps4(c, field)) return SWCU_OK;
+        if (field >= SWCU_F_DX && field <= SWCU_F_RLH_S) c->metrics_dirty = true;
+        RC(launch_fill4(c->w, c->h, c->pitch, F4(c, field), (float)value, c->st));
+        c->launches++;
+        return SWCU_OK;
+    }
+    set_error("unknown field id %d", field);
+    return SWCU_ERR_ARG;
+}
+
+int swcu_copy_field(swcu_ctx *c, int dst_field, int src_field)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    if (!is_f8(dst_field) || !is_f8(src_field)) { set_error("copy_field works on real(8) fields"); return SWCU_ERR_ARG; }
+    Use use(c->device);
+    const bool fused = c->p.mode == SWCU_MODE_FUSED;
+    const bool tr_dst = c->p.use_tracers && (dst_field == SWCU_F_FF1 || dst_field == SWCU_F_FF1P);
+    if (fused && !fused_keeps8(c, dst_field) && !tr_dst) return SWCU_OK;  // e.g. sshn: not resident, derived
+    const double *src = c->f8[src_field];
+    double *dst = c->f8[dst_field];
+    if (!src || !dst) { set_error("field not resident"); return SWCU_ERR_STATE; }
+    SWCU_CUDA(cudaMemcpyAsync(dst, src, c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    if (fused && (state_slot(dst_field) >= 0 || tr_dst)) c->alt_dirty = true;
+    return SWCU_OK;
+}
+
 int swcu_halo_plan(const swcu_dims *d, int nrows, int side, int *send_row, int *recv_row)
 {
     if (!d || !send_row || !recv_row || nrows < 1 || nrows > 2 || (side != 0 && side != 1)) {

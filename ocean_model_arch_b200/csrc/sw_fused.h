@@ -64,4 +64,12 @@ int launch_selftest_mdiv(long n, unsigned long long seed, unsigned long long *ba
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 
+// device-side input construction (sw_init.cu)
+int launch_init_lu(const Geo &g, int w, int h, int nx, int ny, const int *land_dev, unsigned char *lu_dev, cudaStream_t st);
+int launch_init_masks(const Geo &g, int w, int h, const unsigned char *lu_dev, unsigned char *bits, float *const f[7],
+                      cudaStream_t st);
+int launch_expand_rows(const Geo &g, int w, int h, int nx, float *const dst[9], const float *prof_dev, cudaStream_t st);
+int launch_fill8(int w, int h, int pitch, double *dst, double value, cudaStream_t st);
+int launch_fill4(int w, int h, int pitch, float *dst, float value, cudaStream_t st);
+
 }  // namespace swcu

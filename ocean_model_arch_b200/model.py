@@ -253,6 +253,47 @@ class DeviceBlock:
             del inp
         self.hh_init()
 
+    def init_on_device(self, basin, sw, mask=None, *, hhq_rest=100.0, keep_mu=False, r_diss=0.0, stripe_rows=1024):
+        """init_grid_data + init_ocean_data (control/init_data.f90:29-125) with the static inputs built ON
+        THE DEVICE (swcu_init_grid / swcu_fill / swcu_copy_field).  Only the Gaussian initial state is
+        evaluated on the host -- libm's exp, `stripe_rows` rows at a time -- and uploaded once; the
+        other time levels are device copies.  Same resident state as upload_inputs(BlockInputs(...))."""
+        L, d = self.L, self.dims
+        b = basin.basin()
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.int32)
+            assert mask.shape == (basin.ny, basin.nx)
+        check(L.swcu_init_grid(self.h, C.byref(b), _ptr(mask) if mask is not None else None))
+        check(L.swcu_fill(self.h, FIELD_ID["hhq_rest"], float(hhq_rest)))            # init_data.f90:112-114
+        if keep_mu:
+            check(L.swcu_fill(self.h, FIELD_ID["mu"], float(sw.lvisc_2)))            # :76 without :77
+        if r_diss:
+            check(L.swcu_fill(self.h, FIELD_ID["r_diss"], float(np.float32(r_diss))))
+        ics = [("ssh", 1.0, ("sshp", "sshn"))]
+        if sw.use_tracers > 0:
+            ics.append(("ff1", 0.5, ("ff1p", "ff1n")))                             # :80-90
+        h, w = d.shape
+        for a in range(0, h, stripe_rows):
+            rows = min(stripe_rows, h - a)
+            n1, n2 = d.bnd_y1 + a, d.bnd_y1 + a + rows - 1
+            sd = SwcuDims(d.nx_start, d.nx_end, n1, n2, d.bnd_x1, d.bnd_x2, n1, n2)
+            lu = np.zeros((rows, w), dtype=np.float32)
+            check(L.swh_masks(C.byref(b), C.byref(sd), _ptr(mask) if mask is not None else None, _ptr(lu),
+                              None, None, None, None, None, None))
+            wide = SwcuDims(max(d.bnd_x1, 3), min(d.bnd_x2, basin.nx - 2), max(n1, 3), min(n2, basin.ny - 2),
+                            d.bnd_x1, d.bnd_x2, n1, n2)
+            for name, sigma, _ in ics:
+                f = np.zeros((rows, w), dtype=np.float64)
+                if wide.ny_start <= wide.ny_end:
+                    check(L.swh_gaussian(C.byref(wide), _ptr(lu), _ptr(f), sigma, basin.nx // 2, basin.ny // 2))
+                if f.any():
+                    self.upload_rows(name, f, a)
+        for name, _, copies in ics:
+            for c in copies:
+                check(L.swcu_copy_field(self.h, FIELD_ID[c], FIELD_ID[name]))
+        self.hh_init()
+        check(L.swcu_synchronize(self.h, None))
+
     def upload_inputs(self, inp: BlockInputs):
         for name, arr in inp.f.items():
             if name == "r_diss" and not arr.any():
@@ -350,7 +391,7 @@ class ShallowWaterModel:
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, mask=None,
                  device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0,
-                 stripe_rows=None):
+                 stripe_rows=None, device_init=False):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
@@ -359,7 +400,11 @@ class ShallowWaterModel:
             mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
         self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
         self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode)
-        if stripe_rows:
+        if device_init:
+            self.inputs = None
+            self.block.init_on_device(self.basin, self.sw, mask, hhq_rest=hhq_rest, keep_mu=keep_mu, r_diss=r_diss,
+                                      stripe_rows=stripe_rows or 1024)
+        elif stripe_rows:
             self.inputs = None
             self.block.upload_inputs_striped(self.basin, self.sw, mask, stripe_rows, hhq_rest=hhq_rest, keep_mu=keep_mu,
                                              r_diss=r_diss)
