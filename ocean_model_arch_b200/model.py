@@ -471,7 +471,8 @@ class BlockGridModel:
     eight neighbours and step in lockstep through swcu_step_group."""
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, bnx=1, bny=1, mask=None,
-                 devices=(0,), mode=MODE_FUSED, hhq_rest=100.0, keep_mu=False, r_diss=0.0):
+                 devices=(0,), mode=MODE_FUSED, hhq_rest=100.0, keep_mu=False, r_diss=0.0, skip_land_blocks=True,
+                 device_init=False):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
@@ -479,12 +480,23 @@ class BlockGridModel:
         if mask is None and self.basin.mask_file_name != "none":
             mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
         self.grid = {}
+        self.land_blocks = []
         for bn in range(bny):
             for bm in range(bnx):
                 d = block_dims(self.basin.nx, self.basin.ny, bnx, bny, bm, bn)
-                blk = DeviceBlock(d, self.sw, device=devices[(bn * bnx + bm) % len(devices)], mode=mode)
-                blk.upload_inputs(BlockInputs(self.basin, self.sw, d, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
-                                              r_diss=r_diss))
+                # Blocks without a single sea cell get no context, like bglob_proc = -1 in the reference
+                # (core/decomposition.f90:515-521,576-580): their cells never change and their neighbours'
+                # halo cells towards them keep the uploaded (land) values.
+                if skip_land_blocks and mask is not None and \
+                        np.all(np.asarray(mask)[d.ny_start - 1:d.ny_end, d.nx_start - 1:d.nx_end] != 0):
+                    self.land_blocks.append((bm, bn))
+                    continue
+                blk = DeviceBlock(d, self.sw, device=devices[len(self.grid) % len(devices)], mode=mode)
+                if device_init:
+                    blk.init_on_device(self.basin, self.sw, mask, hhq_rest=hhq_rest, keep_mu=keep_mu, r_diss=r_diss)
+                else:
+                    blk.upload_inputs(BlockInputs(self.basin, self.sw, d, mask, hhq_rest=hhq_rest, keep_mu=keep_mu,
+                                                  r_diss=r_diss))
                 self.grid[(bm, bn)] = blk
         for (bm, bn), blk in self.grid.items():   # each pair once: E, N, NE, NW of every block
             for dm, dn in ((1, 0), (0, 1), (1, 1), (-1, 1)):

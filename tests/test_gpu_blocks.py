@@ -52,6 +52,26 @@ def test_block_grid_tiled_path_at_size(swlib, cuda_device):
     many.close()
 
 
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_FUSED])
+def test_land_only_blocks_get_no_context(swlib, cuda_device, mode):
+    """The reference drops blocks without sea cells from the decomposition (bglob_proc = -1,
+    core/decomposition.f90:515-521,576-580); results do not change."""
+    nx, ny = 124, 84
+    mask = basins.island_mask(nx, ny)
+    mask[:, :45] = 1                       # a continent over the western third
+    mask[42:, :82] = 1                     # ... and over the northern part of the middle third
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    m = model.BlockGridModel(model.BasinPar(nx=nx, ny=ny), bnx=3, bny=2, mask=mask, mode=mode, keep_mu=True,
+                             device_init=(mode == MODE_FUSED))
+    assert sorted(m.land_blocks) == [(0, 0), (0, 1), (1, 1)] and len(m.blocks) == 3
+    o.step(40); m.step(40)
+    assert m.synchronize() == 0
+    for f in STATE:
+        assert np.array_equal(inner(m.get(f)), inner(o.get(f))), (f, mode)
+    assert np.abs(o.get("ubrtr")).max() > 1e-6
+    m.close()
+
+
 def test_reference_loop_over_blocks_with_per_block_syncs(swlib, cuda_device):
     """The reference's envoke (core/kernel_interface.f90:48-119): kernel on every block, then the sync of
     every block, driven per block through swcu_envoke_kernel / swcu_envoke_sync on linked contexts."""
