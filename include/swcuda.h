@@ -340,6 +340,20 @@ int swh_gaussian(const swcu_dims *d, const float *lu, double *ssh, double sigma,
 /* block_uniform_decomposition (core/decomposition.f90:427-503): interior start/size of block
  * `i` of `nb` along an axis of `ncells` computational cells. */
 int swh_uniform_split(int ncells, int nb, int i, int *start, int *size);
+/* Which rank (or GPU of one process) owns which block of a bnx x bny block grid; arrays are indexed
+ * [bn*bnx + bm] with 0-based block coordinates.
+ *   swh_block_weights      bglob_weight = sea cells per block (core/decomposition.f90:505-520);
+ *                          mask as for swh_masks (NULL = "none")
+ *   swh_hilbert_d2xy       shared/mpp/hilbert_curve.f90:13-61
+ *   swh_hilbert_partition  create_hilbert_curve_decomposition (core/decomposition.f90:532-612):
+ *                          needs bnx = bny = 2^M; consecutive pieces of the Hilbert walk with about
+ *                          equal weight; `powers` = compute_powers per rank or NULL
+ *   swh_uniform_partition  create_uniform_decomposition (core/decomposition.f90:614-670)
+ * owner = -1 marks a land-only block (no rank holds it). */
+int swh_block_weights(int nx, int ny, int bnx, int bny, const int *mask, double *weights);
+int swh_hilbert_d2xy(int order, int d, int *x, int *y);
+int swh_hilbert_partition(int nb, const double *weights, int nranks, const double *powers, int *owner);
+int swh_uniform_partition(int bnx, int bny, int px, int py, const double *weights, int *owner);
 
 /* ------------------------------------------------------------------------------------------
  * Device-side construction of a resident context's static inputs: init_grid_data

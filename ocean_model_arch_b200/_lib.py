@@ -103,6 +103,10 @@ _SIGNATURES = {
     "swcu_comm_destroy": [_P],
     "swcu_halo_plan": [_DIMS, _I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swcu_halo_exchange": [_P, _I],
+    "swh_block_weights": [_I, _I, _I, _I, _P, _P],
+    "swh_hilbert_d2xy": [_I, _I, C.POINTER(_I), C.POINTER(_I)],
+    "swh_hilbert_partition": [_I, _P, _I, _P, _P],
+    "swh_uniform_partition": [_I, _I, _I, _I, _P, _P],
     "swcu_init_grid": [_P, _P, _P],
     "swcu_fill": [_P, _I, _D],
     "swcu_copy_field": [_P, _I, _I],

@@ -168,4 +168,97 @@ int swh_uniform_split(int ncells, int nb, int i, int *start, int *size)
     return SWCU_OK;
 }
 
+// bglob_weight of block_uniform_decomposition (core/decomposition.f90:505-520, without
+// _DD_BINARY_BLOCK_WEIGHTS_): the number of sea cells in each block's interior.
+int swh_block_weights(int nx, int ny, int bnx, int bny, const int *mask, double *weights)
+{
+    if (!weights || nx < 5 || ny < 5 || bnx < 1 || bny < 1) return SWCU_ERR_ARG;
+    for (int bn = 0; bn < bny; ++bn) {
+        int ys = 0, yn = 0;
+        if (int rc = swh_uniform_split(ny - 4, bny, bn, &ys, &yn)) return rc;
+        for (int bm = 0; bm < bnx; ++bm) {
+            int xs = 0, xn = 0;
+            if (int rc = swh_uniform_split(nx - 4, bnx, bm, &xs, &xn)) return rc;
+            double wgt = 0.0;
+            if (!mask) wgt = (double)xn * (double)yn;  // "none": every interior cell is sea
+            else
+                for (int n = 3 + ys; n < 3 + ys + yn; ++n)
+                    for (int m = 3 + xs; m < 3 + xs + xn; ++m)
+                        wgt += mask[(size_t)(n - 1) * nx + (m - 1)] == 0 ? 1.0 : 0.0;
+            weights[(size_t)bn * bnx + bm] = wgt;
+        }
+    }
+    return SWCU_OK;
+}
+
+// Cell number d of the Hilbert curve of order `order` (shared/mpp/hilbert_curve.f90:13-61, the
+// classic quadrant walk: at each scale pick the quadrant from two bits of d, undo its rotation).
+int swh_hilbert_d2xy(int order, int d, int *x, int *y)
+{
+    if (order < 0 || order > 15 || d < 0 || !x || !y) return SWCU_ERR_ARG;
+    int px = 0, py = 0;
+    for (int side = 1, rest = d; side < (1 << order); side *= 2, rest /= 4) {
+        const int qx = (rest >> 1) & 1, qy = (rest ^ qx) & 1;
+        if (qy == 0) {                 // quadrants 0 and 3 are transposed, 3 is also mirrored
+            if (qx == 1) { px = side - 1 - px; py = side - 1 - py; }
+            const int t = px; px = py; py = t;
+        }
+        px += side * qx; py += side * qy;
+    }
+    *x = px; *y = py;
+    return SWCU_OK;
+}
+
+// create_hilbert_curve_decomposition (core/decomposition.f90:532-612): walk the nb x nb blocks along
+// the Hilbert curve and cut the walk into `nranks` consecutive pieces of about equal weight
+// (piece i aims at the remaining weight times power_i / sum of the remaining powers; a block goes to
+// the next piece when the piece with and without it straddles that mean).  owner[bn*nb + bm] = rank,
+// -1 for blocks of zero weight.  `powers` may be NULL (all ranks equal).
+int swh_hilbert_partition(int nb, const double *weights, int nranks, const double *powers, int *owner)
+{
+    if (!weights || !owner || nb < 1 || nranks < 1) return SWCU_ERR_ARG;
+    int order = 0;
+    while ((1 << order) < nb) ++order;
+    if ((1 << order) != nb) return SWCU_ERR_ARG;   // "Can`t build Hilbert curve for this geometry"
+    auto power_from = [&](int i) { double s = 0.0; for (int k = i; k < nranks; ++k) s += powers ? powers[k] : 1.0; return s; };
+    auto power = [&](int i) { return powers ? powers[i] : 1.0; };
+    double total = 0.0;
+    for (int k = 0; k < nb * nb; ++k) total += weights[k];
+    double mean = total * power(0) / power_from(0), piece = 0.0, assigned = 0.0;
+    int rank = 0;
+    for (int d = 0; d < nb * nb; ++d) {
+        int bm = 0, bn = 0;
+        swh_hilbert_d2xy(order, d, &bm, &bn);
+        const size_t k = (size_t)bn * nb + bm;
+        const double wgt = weights[k];
+        if (wgt == 0.0) { owner[k] = -1; continue; }
+        piece += wgt;
+        if (piece + (piece - wgt) > 2.0 * mean) {
+            if (rank + 1 < nranks) {
+                ++rank;
+                mean = (total - assigned) * power(rank) / power_from(rank);
+            }   // else: the reference keeps everything that is left on the last rank
+            piece = wgt;
+        }
+        owner[k] = rank;
+        assigned += wgt;
+    }
+    return SWCU_OK;
+}
+
+// create_uniform_decomposition (core/decomposition.f90:614-670): a px x py process grid, each rank
+// owning a (bnx/px) x (bny/py) rectangle of blocks; rank = cart rank with y fastest (MPI_Cart_create
+// row-major over (x, y)); -1 for blocks of zero weight.
+int swh_uniform_partition(int bnx, int bny, int px, int py, const double *weights, int *owner)
+{
+    if (!owner || bnx < 1 || bny < 1 || px < 1 || py < 1 || bnx % px || bny % py) return SWCU_ERR_ARG;
+    const int lx = bnx / px, ly = bny / py;
+    for (int bn = 0; bn < bny; ++bn)
+        for (int bm = 0; bm < bnx; ++bm) {
+            const size_t k = (size_t)bn * bnx + bm;
+            owner[k] = (weights && weights[k] == 0.0) ? -1 : (bm / lx) * py + (bn / ly);
+        }
+    return SWCU_OK;
+}
+
 }  // extern "C"

@@ -138,6 +138,36 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def block_weights(nx, ny, bnx, bny, mask=None):
+    """bglob_weight(bm, bn): sea cells per block (core/decomposition.f90:505-520), shape (bny, bnx)."""
+    w = np.zeros((bny, bnx), dtype=np.float64)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=np.int32)
+        assert mask.shape == (ny, nx)
+    check(_lib.lib().swh_block_weights(nx, ny, bnx, bny, _ptr(mask) if mask is not None else None, _ptr(w)))
+    return w
+
+
+def hilbert_partition(weights, nranks, powers=None):
+    """create_hilbert_curve_decomposition (core/decomposition.f90:532-612): owner rank per block, shape like
+    `weights` (bny, bnx) with bnx = bny = 2^M; -1 = land-only block."""
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    assert w.ndim == 2 and w.shape[0] == w.shape[1]
+    owner = np.zeros(w.shape, dtype=np.int32)
+    pw = None if powers is None else np.ascontiguousarray(powers, dtype=np.float64)
+    check(_lib.lib().swh_hilbert_partition(w.shape[0], _ptr(w), int(nranks), _ptr(pw) if pw is not None else None,
+                                           _ptr(owner)))
+    return owner
+
+
+def uniform_partition(weights, px, py):
+    """create_uniform_decomposition (core/decomposition.f90:614-670) on a px x py process grid."""
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    owner = np.zeros(w.shape, dtype=np.int32)
+    check(_lib.lib().swh_uniform_partition(w.shape[1], w.shape[0], int(px), int(py), _ptr(w), _ptr(owner)))
+    return owner
+
+
 # ----------------------------------------------------------------------------- host inputs
 class BlockInputs:
     """What init_grid_data + init_ocean_data leave in grid_data / ocean_data for one block
@@ -472,13 +502,22 @@ class BlockGridModel:
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, bnx=1, bny=1, mask=None,
                  devices=(0,), mode=MODE_FUSED, hhq_rest=100.0, keep_mu=False, r_diss=0.0, skip_land_blocks=True,
-                 device_init=False):
+                 device_init=False, decomposition="round_robin"):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
         self.bnx, self.bny = bnx, bny
         if mask is None and self.basin.mask_file_name != "none":
             mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
+        # which GPU holds which block: parallel.par mod_decomposition 0 (uniform rectangles) / 1 (pieces of
+        # the Hilbert walk balanced by sea cells), with the devices in the role of the ranks
+        self.owner = None
+        if decomposition in ("hilbert", "uniform"):
+            wts = block_weights(self.basin.nx, self.basin.ny, bnx, bny, mask)
+            self.owner = hilbert_partition(wts, len(devices)) if decomposition == "hilbert" else \
+                uniform_partition(wts, 1, len(devices))
+        elif decomposition != "round_robin":
+            raise ValueError(decomposition)
         self.grid = {}
         self.land_blocks = []
         for bn in range(bny):
@@ -491,7 +530,8 @@ class BlockGridModel:
                         np.all(np.asarray(mask)[d.ny_start - 1:d.ny_end, d.nx_start - 1:d.nx_end] != 0):
                     self.land_blocks.append((bm, bn))
                     continue
-                blk = DeviceBlock(d, self.sw, device=devices[len(self.grid) % len(devices)], mode=mode)
+                dev = devices[len(self.grid) % len(devices)] if self.owner is None else devices[max(self.owner[bn, bm], 0)]
+                blk = DeviceBlock(d, self.sw, device=dev, mode=mode)
                 if device_init:
                     blk.init_on_device(self.basin, self.sw, mask, hhq_rest=hhq_rest, keep_mu=keep_mu, r_diss=r_diss)
                 else:

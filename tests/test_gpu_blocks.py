@@ -72,6 +72,26 @@ def test_land_only_blocks_get_no_context(swlib, cuda_device, mode):
     m.close()
 
 
+def test_hilbert_decomposition_of_a_4x4_block_grid(swlib, cuda_device):
+    """mod_decomposition = 1: blocks dealt to the GPUs of this process as balanced pieces of the Hilbert walk
+    (all visible GPUs; with one GPU every piece lands on it).  The answer does not depend on the cut."""
+    import torch
+    nx, ny = 132, 100
+    mask = basins.island_mask(nx, ny)
+    mask[:, :36] = 1
+    ndev = min(torch.cuda.device_count(), 4)
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    m = model.BlockGridModel(model.BasinPar(nx=nx, ny=ny), bnx=4, bny=4, mask=mask, keep_mu=True,
+                             devices=tuple(range(ndev)), decomposition="hilbert", device_init=True)
+    assert (m.owner == -1).sum() == len(m.land_blocks) >= 4
+    assert set(np.unique(m.owner[m.owner >= 0])) == set(range(ndev))
+    o.step(40); m.step(40)
+    assert m.synchronize() == 0
+    for f in STATE:
+        assert np.array_equal(inner(m.get(f)), inner(o.get(f))), f
+    m.close()
+
+
 def test_reference_loop_over_blocks_with_per_block_syncs(swlib, cuda_device):
     """The reference's envoke (core/kernel_interface.f90:48-119): kernel on every block, then the sync of
     every block, driven per block through swcu_envoke_kernel / swcu_envoke_sync on linked contexts."""

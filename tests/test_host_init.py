@@ -94,3 +94,65 @@ def test_uniform_split_matches_reference_rule(swlib):
             assert size == expect
             tot += size
         assert tot == n
+
+
+# ---- block -> rank assignment (core/decomposition.f90:505-670, shared/mpp/hilbert_curve.f90) ---------------
+def _ref_d2xy(m, d):
+    """Test-side restatement of hilbert_d2xy / hilbert_rot as the reference writes them."""
+    n, x, y, t, s = 2 ** m, 0, 0, d, 1
+    while s < n:
+        rx = (t // 2) % 2
+        ry = t % 2 if rx == 0 else (t ^ rx) % 2
+        if ry == 0:
+            if rx == 1:
+                x, y = s - 1 - x, s - 1 - y
+            x, y = y, x
+        x, y, t, s = x + s * rx, y + s * ry, t // 4, s * 2
+    return x, y
+
+
+def test_hilbert_curve(swlib):
+    import ctypes as C
+    for order in range(0, 6):
+        n = 1 << order
+        seen, prev = set(), None
+        for d in range(n * n):
+            x, y = C.c_int(), C.c_int()
+            assert swlib.swh_hilbert_d2xy(order, d, C.byref(x), C.byref(y)) == 0
+            assert (x.value, y.value) == _ref_d2xy(order, d)
+            assert 0 <= x.value < n and 0 <= y.value < n
+            if prev is not None:
+                assert abs(x.value - prev[0]) + abs(y.value - prev[1]) == 1     # a walk over neighbours
+            prev = (x.value, y.value)
+            seen.add(prev)
+        assert len(seen) == n * n
+
+
+def test_block_weights_and_partitions(swlib):
+    nx, ny, nb = 260, 196, 8
+    mask = basins.island_mask(nx, ny)
+    mask[:, :70] = 1                                                   # a continent: land-only blocks
+    w = model.block_weights(nx, ny, nb, nb, mask)
+    assert w.sum() == (mask[2:-2, 2:-2] == 0).sum()
+    d = model.block_dims(nx, ny, nb, nb, 5, 2)
+    assert w[2, 5] == (mask[d.ny_start - 1:d.ny_end, d.nx_start - 1:d.nx_end] == 0).sum()
+    assert model.block_weights(nx, ny, nb, nb, None).sum() == (nx - 4) * (ny - 4)
+    for nranks in (1, 3, 4, 7):
+        own = model.hilbert_partition(w, nranks)
+        assert np.array_equal(own == -1, w == 0) and (w == 0).sum() >= 8
+        walk = []
+        for k in range(nb * nb):
+            x, y = _ref_d2xy(3, k)
+            if own[y, x] >= 0:
+                walk.append(own[y, x])
+        assert walk[0] == 0 and all(b - a in (0, 1) for a, b in zip(walk, walk[1:]))   # consecutive pieces
+        assert walk[-1] == nranks - 1                                                   # every rank got a piece
+        load = np.array([w[own == r].sum() for r in range(nranks)])
+        assert load.max() <= 1.35 * w.sum() / nranks, load                              # balanced by sea cells
+    heavy = model.hilbert_partition(w, 2, powers=[3.0, 1.0])                            # compute_powers
+    assert w[heavy == 0].sum() > 2.0 * w[heavy == 1].sum()
+    uni = model.uniform_partition(w, 2, 4)
+    assert uni[0, 7] == 1 * 4 + 0 and uni[7, 7] == 1 * 4 + 3 and uni[3, 1] == -1 and uni[3, 2] == 0 * 4 + 1
+    assert set(np.unique(uni)) <= set(range(-1, 8))
+    with pytest.raises(Exception):
+        model.hilbert_partition(np.ones((6, 6)), 2)                                     # needs 2^M blocks a side
