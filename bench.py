@@ -310,6 +310,8 @@ def main():
                     "step_bytes_per_cell_launched": bpc if tiled else B_UPDATE + B_PREP,
                     "step_frac_vs_reference_granularity_1196B": B_REF_STEP * (value / world) / 1e9 / peak,
                     "step_frac_vs_floor_196B": B_MIN_STEP * (value / world) / 1e9 / peak}
+            if mask is not None and tiled:
+                roof["note"] = "CTAs of all-land 32x8 tiles exit before any load; their cells are still counted here"
             if not tiled:
                 prep_ms = t_prep.value / steps_prof
                 roof["other_kernels"] = {"k_prep (K10/K2+K3+K5 fused)": {
