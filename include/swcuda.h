@@ -350,6 +350,13 @@ int swh_uniform_split(int ncells, int nb, int i, int *start, int *size);
  *                          equal weight; `powers` = compute_powers per rank or NULL
  *   swh_uniform_partition  create_uniform_decomposition (core/decomposition.f90:614-670)
  * owner = -1 marks a land-only block (no rank holds it). */
+/*   swh_balanced_slabs     y-slabs (one block per GPU) of about equal work instead of equal height: the
+ *                          same sea-weight idea applied to the slab cut.  Work = tiles of
+ *                          tile_cols x band_rows cells; an all-land tile (which the fused step skips)
+ *                          counts `land_cost` of a tile with sea.  Cuts fall on band boundaries.
+ *                          start[r], size[r] (r < nranks) as in swh_uniform_split. */
+int swh_balanced_slabs(int nx, int ny, const int *mask, int nranks, int band_rows, int tile_cols, double land_cost,
+                       int *start, int *size);
 int swh_block_weights(int nx, int ny, int bnx, int bny, const int *mask, double *weights);
 int swh_hilbert_d2xy(int order, int d, int *x, int *y);
 int swh_hilbert_partition(int nb, const double *weights, int nranks, const double *powers, int *owner);

@@ -103,6 +103,7 @@ _SIGNATURES = {
     "swcu_comm_destroy": [_P],
     "swcu_halo_plan": [_DIMS, _I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swcu_halo_exchange": [_P, _I],
+    "swh_balanced_slabs": [_I, _I, _P, _I, _I, _I, _D, _P, _P],
     "swh_block_weights": [_I, _I, _I, _I, _P, _P],
     "swh_hilbert_d2xy": [_I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swh_hilbert_partition": [_I, _P, _I, _P, _P],

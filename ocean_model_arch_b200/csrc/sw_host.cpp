@@ -261,4 +261,44 @@ int swh_uniform_partition(int bnx, int bny, int px, int py, const double *weight
     return SWCU_OK;
 }
 
+// y-slabs of about equal WORK instead of equal height: the sea-weight balancing of the reference's
+// load-balanced decomposition (core/decomposition.f90:505-520,560-600) applied to the one-block-per-GPU
+// slab cut.  The unit of work is what the fused step really skips: a tile_cols x band_rows tile
+// whose cells are all land costs `land_cost` of a tile with sea in it.  Rows are cut at band
+// boundaries counted from the first computational row, so every slab's tile grid coincides with the
+// global one.  start/size as in swh_uniform_split (offsets in computational rows), for all ranks.
+int swh_balanced_slabs(int nx, int ny, const int *mask, int nranks, int band_rows, int tile_cols, double land_cost,
+                       int *start, int *size)
+{
+    if (!start || !size || nx < 5 || ny < 5 || nranks < 1 || band_rows < 1 || tile_cols < 1) return SWCU_ERR_ARG;
+    const int rows = ny - 4, cols = nx - 4;
+    const int nbands = (rows + band_rows - 1) / band_rows, ntx = (cols + tile_cols - 1) / tile_cols;
+    if (nbands < nranks) return SWCU_ERR_ARG;
+    std::vector<double> w((size_t)nbands, 0.0);
+    double total = 0.0;
+    for (int b = 0; b < nbands; ++b) {
+        const int n0 = 3 + b * band_rows, n1 = imin(n0 + band_rows - 1, ny - 2);
+        for (int t = 0; t < ntx; ++t) {
+            const int m0 = 3 + t * tile_cols, m1 = imin(m0 + tile_cols - 1, nx - 2);
+            bool sea = mask == nullptr;
+            for (int n = n0; n <= n1 && !sea; ++n)
+                for (int m = m0; m <= m1 && !sea; ++m) sea = mask[(size_t)(n - 1) * nx + (m - 1)] == 0;
+            w[b] += sea ? 1.0 : land_cost;
+        }
+        total += w[b];
+    }
+    int b = 0;
+    double cum = 0.0;
+    for (int r = 0; r < nranks; ++r) {
+        const int first = b;
+        const double target = total * (double)(r + 1) / (double)nranks;
+        // at least one band each, and leave one band for every rank still to come
+        do { cum += w[b]; ++b; } while (b < nbands - (nranks - 1 - r) && cum + 0.5 * w[b] <= target);
+        if (r == nranks - 1) b = nbands;
+        start[r] = first * band_rows;
+        size[r] = imin(b * band_rows, rows) - start[r];
+    }
+    return SWCU_OK;
+}
+
 }  // extern "C"

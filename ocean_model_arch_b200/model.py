@@ -138,6 +138,20 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def balanced_slab_dims(nx, ny, world, rank, mask=None, band_rows=8, tile_cols=32, land_cost=0.03):
+    """Block `rank` of `world` y-slabs cut for equal work (swh_balanced_slabs): slabs with much land get more
+    rows.  Deterministic, so every rank computes the same cut."""
+    ys = np.zeros(world, dtype=np.int32)
+    yn = np.zeros(world, dtype=np.int32)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, dtype=np.int32)
+        assert mask.shape == (ny, nx)
+    check(_lib.lib().swh_balanced_slabs(nx, ny, _ptr(mask) if mask is not None else None, world, band_rows, tile_cols,
+                                        float(land_cost), _ptr(ys), _ptr(yn)))
+    y0 = 3 + int(ys[rank])
+    return SwcuDims(3, nx - 2, y0, y0 + int(yn[rank]) - 1, 1, nx, y0 - 2, y0 + int(yn[rank]) + 1)
+
+
 def block_weights(nx, ny, bnx, bny, mask=None):
     """bglob_weight(bm, bn): sea cells per block (core/decomposition.f90:505-520), shape (bny, bnx)."""
     w = np.zeros((bny, bnx), dtype=np.float64)
@@ -421,14 +435,17 @@ class ShallowWaterModel:
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, mask=None,
                  device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0,
-                 stripe_rows=None, device_init=False):
+                 stripe_rows=None, device_init=False, balance=False):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
         self.rank, self.world = rank, world
         if mask is None and self.basin.mask_file_name != "none":
             mask = read_mask_file(self.basin.mask_file_name, self.basin.nx, self.basin.ny)
-        self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
+        if balance and world > 1:   # slabs of equal work (sea-weight balancing) instead of equal height
+            self.dims = balanced_slab_dims(self.basin.nx, self.basin.ny, world, rank, mask)
+        else:
+            self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
         self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode)
         if device_init:
             self.inputs = None

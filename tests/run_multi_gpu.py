@@ -27,6 +27,7 @@ def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 203
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    balance = len(sys.argv) > 4 and sys.argv[4] == "balance"   # slabs of equal work instead of equal height
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -37,7 +38,7 @@ def main():
     # the reference's sync_test (shared/mpp/syncborder_block2D_gen_test.fi:10-97): interiors hold i*j, after
     # the halo exchange every halo row a neighbour owns must hold i*j too
     for mode, nrows in ((MODE_FUSED, 2), (MODE_REFERENCE, 1)):
-        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world)
+        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, balance=balance)
         ids = [model.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         m.attach_comm(ids[0])
@@ -61,7 +62,8 @@ def main():
         m.block.close()
         dist.barrier()
     for mode, tiled in ((MODE_FUSED, 1), (MODE_FUSED, 0), (MODE_REFERENCE, 0)):
-        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True)
+        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True,
+                                    balance=balance, device_init=balance)
         if mode == MODE_FUSED:
             m.block.set_option("tiled", tiled)
         ids = [model.comm_unique_id() if rank == 0 else None]

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("shape", [(150, 203, 40), (77, 64, 25)])
+@pytest.mark.parametrize("shape", [(150, 203, 40), (77, 64, 25), (150, 203, 40, "balance")],
+                         ids=["150x203", "77x64", "150x203-balanced-slabs"])
 def test_slabs_over_nccl_bitwise(swlib, cuda_device, shape):
     import torch
     n = torch.cuda.device_count()

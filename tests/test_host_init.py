@@ -156,3 +156,28 @@ def test_block_weights_and_partitions(swlib):
     assert set(np.unique(uni)) <= set(range(-1, 8))
     with pytest.raises(Exception):
         model.hilbert_partition(np.ones((6, 6)), 2)                                     # needs 2^M blocks a side
+
+
+def test_balanced_slabs(swlib):
+    nx, ny = 260, 404
+    mask = basins.island_mask(nx, ny)
+    mask[:150, 40:] = 1                                   # the southern third is mostly land
+    for world in (1, 2, 3, 8):
+        ds = [model.balanced_slab_dims(nx, ny, world, r, mask) for r in range(world)]
+        assert ds[0].ny_start == 3 and ds[-1].ny_end == ny - 2
+        for a, b in zip(ds, ds[1:]):
+            assert b.ny_start == a.ny_end + 1 and (b.ny_start - 3) % 8 == 0     # contiguous, cut on tile rows
+        assert all(d.ny_end - d.ny_start + 1 >= 8 for d in ds[:-1])
+        assert all((d.bnd_y1, d.bnd_y2) == (d.ny_start - 2, d.ny_end + 2) for d in ds)
+
+        def work(d):   # tiles with any sea cell
+            sea = mask[d.ny_start - 1:d.ny_end, 2:-2] == 0
+            return sum(sea[j:j + 8, i:i + 32].any() for j in range(0, sea.shape[0], 8) for i in range(0, sea.shape[1], 32))
+        if world > 1:
+            bal = [work(d) for d in ds]
+            uni = [work(model.block_dims(nx, ny, 1, world, 0, r)) for r in range(world)]
+            assert max(bal) <= max(uni)
+            if world in (2, 3):
+                assert max(bal) < 0.8 * max(uni), (bal, uni)          # the land-heavy slab got more rows
+    ds = [model.balanced_slab_dims(nx, ny, 5, r, None) for r in range(5)]       # no mask: near-uniform
+    assert max(d.ny_end - d.ny_start for d in ds) - min(d.ny_end - d.ny_start for d in ds) <= 8
