@@ -178,7 +178,8 @@ enum swcu_field {
 
 /* step structure */
 #define SWCU_MODE_REFERENCE 0 /* the reference's 11-kernel sequence, one launch per kernel (K1..K11) */
-#define SWCU_MODE_FUSED 1     /* 2 launches per step: depth/vorticity/stress prep + update/filter */
+#define SWCU_MODE_FUSED 1     /* the whole step in ONE launch (TMA-tiled; K1..K11 fused), or prep + update
+                               * launches when the grid's metrics vary along x; + one launch for the tracer */
 
 typedef struct swcu_params {
     int full_free_surface, trans_terms, ksw_lat; /* sw.par 1-3 (configs/sw.f90:34-36) */
@@ -221,7 +222,11 @@ int swcu_download_to_device(swcu_ctx *ctx, int field, void *dev);
  * when every one of them is constant along m (carthesian and unrotated spherical grids), 0 = always
  * read the 2-D real(4) arrays.  "tiled": 1 (default) = with metric tables in use, run the whole
  * step as ONE launch of the TMA-staged shared-memory kernel; 0 = two launches (prep + update) from
- * global memory.  Results are bitwise identical in every combination. */
+ * global memory.  "land_skip": 1 (default) = CTAs of the tiled kernel whose 32x8 output cells are all
+ * land exit before loading anything (flags rebuilt after a mask upload), 0 = compute every tile.
+ * "tile_variant": 1..5 selects the tile shape / cells per thread of the tiled kernel (default 4:
+ * 32x8 cells, 128 threads, 2 cells per thread, 4 CTAs per SM).  Results are bitwise identical in every
+ * combination. */
 int swcu_set_option(swcu_ctx *ctx, const char *name, int value);
 /* 1 if the last step used the per-row metric tables, 0 if it read the 2-D arrays. */
 int swcu_uses_metric_tables(const swcu_ctx *ctx);
