@@ -121,6 +121,46 @@ def test_fused_equals_reference_sequence_at_2048(swlib, cuda_device):
     assert np.abs(b.get("ssh")).max() < 0.4
 
 
+def test_config3_size_8192_masked_basin(swlib, cuda_device):
+    """BASELINE config 3 size: 8192^2 cells with the synthetic land mask (carthesian grid).  Far too large
+    for the oracle, so: FUSED (one tiled launch, all-land tiles skipped, inputs built on the device)
+    == REFERENCE (11 kernels, inputs built on the host) bitwise, == the same basin cut into 2 x 2 linked
+    blocks bitwise, and the size-independent properties hold."""
+    n = 8196
+    bp = model.BasinPar(nx=n, ny=n, curve_grid=0)
+    mask = basins.island_mask(n, n, ndisc=12)
+    steps = 10
+    b = model.ShallowWaterModel(bp, mask=mask, mode=MODE_FUSED, device_init=True)
+    ssh0 = b.get("ssh")
+    b.step(steps)
+    assert b.block.synchronize() == 0 and b.block.launches == steps + 4      # + 4 set-up kernels (lu, masks, metric rows, hhq_rest fill)
+    got = {f: b.get(f) for f in STATE}
+    lu = b.get("lu")
+    area = (b.get("dx") * b.get("dy")).astype(np.float64) * lu
+    b.block.close()
+
+    a = model.ShallowWaterModel(bp, mask=mask, mode=MODE_REFERENCE, stripe_rows=1024)
+    a.step(steps)
+    assert a.block.synchronize() == 0
+    for f in STATE:
+        assert np.array_equal(a.get(f), got[f]), f
+    a.block.close()
+
+    g = model.BlockGridModel(bp, bnx=2, bny=2, mask=mask, device_init=True)
+    g.step(steps)
+    assert g.synchronize() == 0
+    for f in ("ssh", "ubrtr", "vbrtrp"):
+        assert np.array_equal(g.get(f)[2:-2, 2:-2], got[f][2:-2, 2:-2]), f
+    g.close()
+
+    ssh = got["ssh"]
+    assert 0.2 < (mask == 1).mean() < 0.3
+    v0, v1 = (ssh0 * area).sum(), (ssh * area).sum()
+    assert abs(v1 - v0) <= 1e-12 * abs(v0)                                    # mass conserved (flux form)
+    assert not ssh[lu < 0.5].any() and not got["ubrtr"][lu < 0.5].any()        # land untouched
+    assert np.isfinite(ssh).all() and np.abs(ssh).max() < 0.4 and np.abs(got["ubrtr"]).max() > 0
+
+
 def test_blowup_flag(swlib, cuda_device):
     from ocean_model_arch_b200._lib import SwcuError
     nx, ny = 40, 30
