@@ -302,6 +302,19 @@ int swcu_halo_plan(const swcu_dims *dims, int nrows, int side, int *send_row, in
  * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use. */
 int swcu_halo_exchange(swcu_ctx *ctx, int field);
 
+/* The same y-slab exchange WITHOUT NCCL, for ranks on one node: every rank exports IPC handles of its
+ * prognostic buffers (swcu_peer_export fills SWCU_PEER_BLOB_BYTES bytes), the host layer hands each blob
+ * to the two neighbouring ranks (MPI_Sendrecv / torch.distributed), and swcu_peer_attach maps them
+ * (side 0 = the block below, 1 = the block above).  Each step the boundary strips are computed
+ * first, one small kernel stores them straight into the neighbours' halo rows over NVLink and
+ * publishes a step counter there; the neighbour's stream waits for that counter with a stream memory
+ * operation (cuStreamWaitValue64), so there is no collective, no copy kernel on the receiving GPU and
+ * no host synchronisation in the step.  FUSED mode; all ranks must step in lockstep (same nsteps).
+ * Mutually exclusive with swcu_comm_init and swcu_link. */
+#define SWCU_PEER_BLOB_BYTES 2048
+int swcu_peer_export(swcu_ctx *ctx, void *blob);
+int swcu_peer_attach(swcu_ctx *ctx, int side, const void *blob);
+
 /* Several blocks per process (parallel.par bppnx x bppny > 1 x 1, and the reference's _GPU_MULTI_
  * one-process-many-GPUs mode): swcu_link ties two contexts of the same process that are neighbours
  * in a tensor-product block grid -- side, or corner; the direction follows from their dims, the

@@ -61,6 +61,8 @@ _P, _D, _I, _V = C.c_void_p, C.c_double, C.c_int, C.c_void_p
 _DIMS = C.POINTER(SwcuDims)
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
+PEER_BLOB_BYTES = 2048   # SWCU_PEER_BLOB_BYTES
+
 _SIGNATURES = {
     "swcu_sw_update_ssh_kernel": [_DIMS, _D] + [_P] * 11 + [_V],
     "swcu_sw_update_uv": [_DIMS, _D] + [_P] * 30 + [_V],
@@ -111,6 +113,8 @@ _SIGNATURES = {
     "swcu_init_grid": [_P, _P, _P],
     "swcu_fill": [_P, _I, _D],
     "swcu_copy_field": [_P, _I, _I],
+    "swcu_peer_export": [_P, _P],
+    "swcu_peer_attach": [_P, _I, _P],
     "swcu_link": [_P, _P],
     "swcu_unlink": [_P],
     "swcu_step_group": [C.POINTER(_P), _I, _D, _I],

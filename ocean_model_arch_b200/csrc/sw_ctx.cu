@@ -14,6 +14,7 @@
 // stream; in FUSED mode the two boundary strips are computed first, their exchange overlaps the
 // interior update (replaces shared/mpp/sync.f90:294-374 + syncborder_block2D_gen_all.fi).
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <cmath>
@@ -94,6 +95,25 @@ int encode_load()
     return SWCU_OK;
 }
 
+// cuStreamWaitValue64 (stream memory operation) through the runtime's driver entry point
+typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+WaitValueFn g_wait_value = nullptr;
+
+int wait_value_load()
+{
+    if (g_wait_value) return SWCU_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuStreamWaitValue64 not available from the driver");
+        cudaGetLastError();
+        return SWCU_ERR_CUDA;
+    }
+    g_wait_value = (WaitValueFn)fn;
+    return SWCU_OK;
+}
+
 #define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
 const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
@@ -141,6 +161,18 @@ struct swcu_ctx {
     swcu_ctx *nbr[8] = {};
     int nlinks = 0;
     FusedArgs fa;  // arguments of the step in flight (FUSED)
+    // halo exchange over peer memory between PROCESSES (swcu_peer_export / swcu_peer_attach)
+    struct PeerLink {
+        bool on = false;
+        double *set[2][8] = {};               // the neighbour's planes, peer-mapped: [set][ssh sshp u up v vp ff1 ff1p]
+        unsigned long long *flags = nullptr;  // the neighbour's flag words, peer-mapped
+        int by1 = 0;
+        std::vector<void *> opened;
+    } peer[2];                                // 0 = below (rank-1), 1 = above (rank+1)
+    unsigned long long *flags = nullptr;      // mine: READY lo/hi, FREE lo/hi, READY_FF lo/hi
+    unsigned *push_count = nullptr;           // CTA counters of k_push_halo (one per stream)
+    double *set_ptr[2][8] = {};               // my planes in export order
+    int cur_set = 0;                          // set_ptr[cur_set] holds the current state
     // per-row metric tables (FUSED): rebuilt after a metric upload, used when all arrays are row-constant
     bool metrics_dirty = true, want_tables = true, use_tables = false;
     double *tab = nullptr;
@@ -443,6 +475,50 @@ int tensor_map_for(swcu_ctx *c, const double *base, CUtensorMap *out)
     return SWCU_OK;
 }
 
+// ---- halo rows over peer memory (processes on one node; swcu_peer_export / swcu_peer_attach) --------
+// Pushes my first / last two interior rows of arrays first .. first+n-1 (export order) of the WRITE
+// set into the neighbours' halo rows of THEIR write set and publishes `tick` in their flag word
+// flag0 + (0: written by the block below them, 1: by the block above).  The push first waits until
+// each neighbour has declared its write buffers free for this step (FREE words 2, 3).
+int peer_push(swcu_ctx *c, cudaStream_t st, int first, int n, unsigned long long tick, int flag0)
+{
+    RC(wait_value_load());
+    PushArgs p = {};
+    const int wset = c->cur_set ^ 1;
+    for (int side = 0; side < 2; ++side) {
+        const swcu_ctx::PeerLink &pl = c->peer[side];
+        if (!pl.on) continue;
+        CUresult r = g_wait_value((CUstream)st, (CUdeviceptr)(c->flags + 2 + side), tick, 0 /* GEQ */);
+        if (r != CUDA_SUCCESS) { set_error("cuStreamWaitValue64 failed with %d", (int)r); return SWCU_ERR_CUDA; }
+        int srow = 0, rrow = 0;
+        RC(swcu_halo_plan(&c->d, 2, side, &srow, &rrow));
+        const long drow = (long)(c->d.bnd_y1 + srow) - pl.by1;   // same global rows in the neighbour's array
+        for (int k = 0; k < n; ++k) {
+            p.src[side][k] = c->set_ptr[wset][first + k] + (size_t)srow * c->pitch;
+            p.dst[side][k] = pl.set[wset][first + k] + (size_t)drow * c->pitch;
+        }
+        p.flag[side] = pl.flags + flag0 + (side == 0 ? 1 : 0);   // I am the block above my lower neighbour
+    }
+    p.value = tick;
+    p.count = 2L * c->pitch;
+    p.counter = c->push_count + (flag0 ? 1 : 0);
+    RC(launch_push_halo(p, n, st));
+    c->launches++;
+    return SWCU_OK;
+}
+
+// makes `st` wait until both neighbours have pushed their rows for this tick (flag words flag0, flag0+1)
+int peer_wait(swcu_ctx *c, cudaStream_t st, int flag0, unsigned long long tick)
+{
+    RC(wait_value_load());
+    for (int side = 0; side < 2; ++side) {
+        if (!c->peer[side].on) continue;
+        CUresult r = g_wait_value((CUstream)st, (CUdeviceptr)(c->flags + flag0 + side), tick, 0 /* GEQ */);
+        if (r != CUDA_SUCCESS) { set_error("cuStreamWaitValue64 failed with %d", (int)r); return SWCU_ERR_CUDA; }
+    }
+    return SWCU_OK;
+}
+
 // The n -> n+1 update of the six prognostic arrays into the write buffers (no tracers, no swap).
 int fused_main(swcu_ctx *c, double tau)
 {
@@ -484,11 +560,13 @@ int fused_main(swcu_ctx *c, double tau)
     const int ns = g.ny_start, ne = g.ny_end;
     const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(g, a);
     // rows of the main launch: everything, or the interior between the two boundary strips
+    // neighbours in other processes: over NCCL (communicator) or over peer memory (swcu_peer_attach)
+    const bool peers = c->peer[0].on || c->peer[1].on;
+    const bool lo = peers ? c->peer[0].on : (c->comm && c->rank > 0);
+    const bool hi = peers ? c->peer[1].on : (c->comm && c->rank + 1 < c->nranks);
     int main0 = ns, main1 = ne;
-    if (c->comm) {
-        if (c->rank > 0) main0 = (ns + 1 < ne ? ns + 1 : ne) + 1;
-        if (c->rank + 1 < c->nranks && main0 <= ne) main1 = (ne - 1 > main0 ? ne - 1 : main0) - 1;
-    }
+    if (lo) main0 = (ns + 1 < ne ? ns + 1 : ne) + 1;
+    if (hi && main0 <= ne) main1 = (ne - 1 > main0 ? ne - 1 : main0) - 1;
     if (tiled && (c->masks_dirty || c->tile_land_n0 != main0 || c->tile_land_n1 != main1)) {
         // (re)build the all-land tile flags of the main launch
         int ntx = 0, nty = 0;
@@ -522,27 +600,38 @@ int fused_main(swcu_ctx *c, double tau)
         c->launches++;
         return SWCU_OK;
     };
-    if (!c->comm) {
+    if (!lo && !hi) {
         RC(rows(ns, ne, c->st));
     } else {
         // The two boundary strips (the rows each neighbour needs) run on a high-priority stream
-        // concurrently with the interior update; their completion releases the NCCL exchange on a
-        // second high-priority stream, and the compute stream joins both before the next step.
-        const bool lo = c->rank > 0, hi = c->rank + 1 < c->nranks;
+        // concurrently with the interior update; their completion releases the exchange on a second
+        // high-priority stream (NCCL) or the push into the neighbours' memory (peer path), and the
+        // compute stream joins before the next step.
+        const unsigned long long tick = (unsigned long long)c->steps_done + 1;
         int i0 = ns, i1 = ne;
+        if (peers)   // my write buffers may be written by the neighbours from here on (alt sync is done)
+            RC(launch_signal(lo ? c->peer[0].flags + 3 : nullptr, hi ? c->peer[1].flags + 2 : nullptr, tick, c->st));
         SWCU_CUDA(cudaEventRecord(c->ev_start, c->st));
         SWCU_CUDA(cudaStreamWaitEvent(c->bnd_st, c->ev_start, 0));
         if (lo) { const int e = ns + 1 < ne ? ns + 1 : ne; RC(rows(ns, e, c->bnd_st)); i0 = e + 1; }
         if (hi && i0 <= ne) { const int s = ne - 1 > i0 ? ne - 1 : i0; RC(rows(s, ne, c->bnd_st)); i1 = s - 1; }
-        SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->bnd_st));
-        SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
-        SWCU_NCCL(g_nccl.GroupStart());
-        for (int i = 0; i < 6; ++i)
-            if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
-        SWCU_NCCL(g_nccl.GroupEnd());
-        SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
-        RC(rows(i0, i1, c->st));
-        SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));  // strips -> exchange -> here
+        if (peers) {
+            RC(peer_push(c, c->bnd_st, 0, 6, tick, 0));
+            SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->bnd_st));
+            RC(rows(i0, i1, c->st));
+            SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_bnd, 0));
+            RC(peer_wait(c, c->st, 0, tick));   // my halo rows of the new state have arrived
+        } else {
+            SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->bnd_st));
+            SWCU_CUDA(cudaStreamWaitEvent(c->comm_st, c->ev_bnd, 0));
+            SWCU_NCCL(g_nccl.GroupStart());
+            for (int i = 0; i < 6; ++i)
+                if (int rc = exchange_rows(c, c->alt[i], 2, c->comm_st)) { g_nccl.GroupEnd(); return rc; }
+            SWCU_NCCL(g_nccl.GroupEnd());
+            SWCU_CUDA(cudaEventRecord(c->ev_comm, c->comm_st));
+            RC(rows(i0, i1, c->st));
+            SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_comm, 0));  // strips -> exchange -> here
+        }
     }
     return SWCU_OK;
 }
@@ -553,7 +642,11 @@ int fused_tracer(swcu_ctx *c)
 {
     RC(launch_tracer(c->g, c->fa, c->g.ny_start, c->g.ny_end, c->st));
     c->launches++;
-    if (c->comm) {
+    if (c->peer[0].on || c->peer[1].on) {
+        const unsigned long long tick = (unsigned long long)c->steps_done + 1;
+        RC(peer_push(c, c->st, 6, 2, tick, 4));
+        RC(peer_wait(c, c->st, 4, tick));
+    } else if (c->comm) {
         SWCU_NCCL(g_nccl.GroupStart());
         int rc = exchange_rows(c, c->alt_ff[0], 2, c->st);
         if (!rc) rc = exchange_rows(c, c->alt_ff[1], 2, c->st);
@@ -572,6 +665,7 @@ void fused_swap(swcu_ctx *c)
         t = c->f8[SWCU_F_FF1P]; c->f8[SWCU_F_FF1P] = c->alt_ff[1]; c->alt_ff[1] = t;
     }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
+    c->cur_set ^= 1;
 }
 
 int step_fused(swcu_ctx *c, double tau)
@@ -914,6 +1008,13 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
         }
         for (int f = 100; f < SWCU_F4_END; ++f) if (fused_keeps4(c, f)) TRY(alloc4(c, f));
         TRY(dev_alloc(c, (void **)&c->mask, c->plane));
+        TRY(dev_alloc(c, (void **)&c->flags, 8 * sizeof(unsigned long long)));
+        TRY(dev_alloc(c, (void **)&c->push_count, 2 * sizeof(unsigned)));
+        for (int i = 0; i < 6; ++i) { c->set_ptr[0][i] = c->f8[kState[i]]; c->set_ptr[1][i] = c->alt[i]; }
+        if (params->use_tracers) {
+            c->set_ptr[0][6] = c->f8[SWCU_F_FF1]; c->set_ptr[0][7] = c->f8[SWCU_F_FF1P];
+            c->set_ptr[1][6] = c->alt_ff[0]; c->set_ptr[1][7] = c->alt_ff[1];
+        }
     }
     TRYCUDA(cudaStreamSynchronize(c->st));
     if (rc) { swcu_destroy(c); return rc; }
@@ -928,6 +1029,9 @@ int swcu_destroy(swcu_ctx *c)
     Use use(c->device);
     cudaDeviceSynchronize();
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto &pl : c->peer)
+        for (void *p : pl.opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->flags); cudaFree(c->push_count);
     for (auto &p : c->f8) cudaFree(p);
     for (auto &p : c->f4) cudaFree(p);
     for (auto &p : c->alt) cudaFree(p);
@@ -1132,7 +1236,7 @@ int swcu_comm_init(swcu_ctx *c, int nranks, int rank, const void *id128)
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad argument"); return SWCU_ERR_ARG; }
     if (c->comm) { set_error("communicator already attached"); return SWCU_ERR_STATE; }
     if (nranks == 1) return SWCU_OK;
-    if (c->nlinks) { set_error("a block has either in-process links or a communicator"); return SWCU_ERR_STATE; }
+    if (c->nlinks || c->peer[0].on || c->peer[1].on) { set_error("a block exchanges halos over ONE of: communicator, in-process links, peer memory"); return SWCU_ERR_STATE; }
     RC(nccl_load());
     Use use(c->device);
     ncclUniqueId id;
@@ -1398,6 +1502,74 @@ int swcu_copy_field(swcu_ctx *c, int dst_field, int src_field)
     if (!src || !dst) { set_error("field not resident"); return SWCU_ERR_STATE; }
     SWCU_CUDA(cudaMemcpyAsync(dst, src, c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     if (fused && (state_slot(dst_field) >= 0 || tr_dst)) c->alt_dirty = true;
+    return SWCU_OK;
+}
+
+namespace {
+struct PeerBlob {
+    unsigned magic;
+    int pid, device;
+    int by1, ny_start, ny_end, pitch, w, tracers, cur_set;
+    long steps_done;
+    cudaIpcMemHandle_t mem[2][8];
+    cudaIpcMemHandle_t flags;
+};
+static_assert(sizeof(PeerBlob) <= SWCU_PEER_BLOB_BYTES, "blob size");
+const unsigned kPeerMagic = 0x53574355u;
+}  // namespace
+
+int swcu_peer_export(swcu_ctx *c, void *blob)
+{
+    if (!c || !blob) { set_error("null argument"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_FUSED) { set_error("the peer-memory halo path needs SWCU_MODE_FUSED"); return SWCU_ERR_STATE; }
+    Use use(c->device);
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kPeerMagic; b.pid = (int)getpid(); b.device = c->device;
+    b.by1 = c->d.bnd_y1; b.ny_start = c->d.ny_start; b.ny_end = c->d.ny_end; b.pitch = c->pitch; b.w = c->w;
+    b.tracers = c->p.use_tracers ? 1 : 0; b.cur_set = c->cur_set; b.steps_done = c->steps_done;
+    const int n = c->p.use_tracers ? 8 : 6;
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < n; ++k) SWCU_CUDA(cudaIpcGetMemHandle(&b.mem[s][k], c->set_ptr[s][k]));
+    SWCU_CUDA(cudaIpcGetMemHandle(&b.flags, c->flags));
+    memset(blob, 0, SWCU_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return SWCU_OK;
+}
+
+int swcu_peer_attach(swcu_ctx *c, int side, const void *blob)
+{
+    if (!c || !blob || (side != 0 && side != 1)) { set_error("bad argument"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_FUSED) { set_error("the peer-memory halo path needs SWCU_MODE_FUSED"); return SWCU_ERR_STATE; }
+    if (c->comm || c->nlinks) { set_error("a block exchanges halos over ONE of: communicator, in-process links, peer memory"); return SWCU_ERR_STATE; }
+    if (c->peer[side].on) { set_error("that side is already attached"); return SWCU_ERR_STATE; }
+    PeerBlob b;
+    memcpy(&b, blob, sizeof(b));
+    if (b.magic != kPeerMagic) { set_error("not a swcu_peer_export blob"); return SWCU_ERR_ARG; }
+    if (b.pid == (int)getpid()) { set_error("blocks of one process are tied with swcu_link"); return SWCU_ERR_ARG; }
+    const bool adjacent = side == 0 ? b.ny_end + 1 == c->d.ny_start : b.ny_start == c->d.ny_end + 1;
+    if (!adjacent || b.pitch != c->pitch || b.w != c->w) { set_error("the exported block is not my y-neighbour on that side"); return SWCU_ERR_ARG; }
+    if (b.tracers != (c->p.use_tracers ? 1 : 0) || b.cur_set != c->cur_set || b.steps_done != c->steps_done) {
+        set_error("neighbours must agree on use_tracers and on the number of steps taken");
+        return SWCU_ERR_STATE;
+    }
+    RC(wait_value_load());
+    Use use(c->device);
+    swcu_ctx::PeerLink &pl = c->peer[side];
+    const int n = c->p.use_tracers ? 8 : 6;
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < n; ++k) {
+            void *p = nullptr;
+            SWCU_CUDA(cudaIpcOpenMemHandle(&p, b.mem[s][k], cudaIpcMemLazyEnablePeerAccess));
+            pl.opened.push_back(p);
+            pl.set[s][k] = (double *)p;
+        }
+    void *f = nullptr;
+    SWCU_CUDA(cudaIpcOpenMemHandle(&f, b.flags, cudaIpcMemLazyEnablePeerAccess));
+    pl.opened.push_back(f);
+    pl.flags = (unsigned long long *)f;
+    pl.by1 = b.by1;
+    pl.on = true;
     return SWCU_OK;
 }
 

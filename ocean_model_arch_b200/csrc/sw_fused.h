@@ -64,6 +64,18 @@ int launch_selftest_mdiv(long n, unsigned long long seed, unsigned long long *ba
 int launch_mask_set(long total, const float *src, unsigned char *bits, int bit, cudaStream_t st);
 int launch_mask_get(long total, float *dst, const unsigned char *bits, int bit, cudaStream_t st);
 
+// halo rows pushed into the neighbours' buffers over peer memory (sw_init.cu)
+struct PushArgs {
+    const double *src[2][8];       // [side][array]: first row to send
+    double *dst[2][8];             // [side][array]: where it lands in the neighbour's plane (peer-mapped)
+    unsigned long long *flag[2];   // the neighbours' "halo ready" words (peer-mapped), or nullptr
+    unsigned long long value;
+    long count;                    // doubles per array and side
+    unsigned *counter;             // zero-initialised CTA counter
+};
+int launch_push_halo(const PushArgs &p, int narrays, cudaStream_t st);
+int launch_signal(unsigned long long *a, unsigned long long *b, unsigned long long value, cudaStream_t st);
+
 // device-side input construction (sw_init.cu)
 int launch_init_lu(const Geo &g, int w, int h, int nx, int ny, const int *land_dev, unsigned char *lu_dev, cudaStream_t st);
 int launch_init_masks(const Geo &g, int w, int h, const unsigned char *lu_dev, unsigned char *bits, float *const f[7],

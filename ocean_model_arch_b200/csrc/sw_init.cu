@@ -80,6 +80,37 @@ __global__ void k_expand_rows(Geo g, int w, int h, int nx, RowFill out, const fl
     for (int k = 0; k < 9; ++k) out.dst[k][c] = prof[((long)k * 2 + inside) * h + j];
 }
 
+// Halo push over peer memory (NVLink): CTA (k, side) copies `count` doubles of array k -- the rows the
+// neighbour on `side` lacks -- from this GPU's buffer into the neighbour's halo rows through a
+// peer-mapped pointer.  The last CTA to finish publishes `value` in both neighbours' flag words
+// (system-scope fence first), which their streams wait on with a stream memory operation.
+__global__ void k_push_halo(PushArgs p)
+{
+    const int k = blockIdx.x, side = blockIdx.y;
+    const double *src = p.src[side][k];
+    double *dst = p.dst[side][k];
+    if (src && dst)
+        for (long i = threadIdx.x; i < p.count; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(p.counter, 1u);
+        if (done == gridDim.x * gridDim.y - 1) {
+            *p.counter = 0;
+            __threadfence_system();
+            for (int s = 0; s < 2; ++s)
+                if (p.flag[s]) *reinterpret_cast<volatile unsigned long long *>(p.flag[s]) = p.value;
+        }
+    }
+}
+
+__global__ void k_signal(unsigned long long *a, unsigned long long *b, unsigned long long value)
+{
+    __threadfence_system();
+    if (a) *reinterpret_cast<volatile unsigned long long *>(a) = value;
+    if (b) *reinterpret_cast<volatile unsigned long long *>(b) = value;
+}
+
 template <typename T>
 __global__ void k_fill(int w, int h, int pitch, T *__restrict__ dst, T value)
 {
@@ -113,6 +144,18 @@ int launch_expand_rows(const Geo &g, int w, int h, int nx, float *const dst[9], 
     for (int k = 0; k < 9; ++k) out.dst[k] = dst[k];
     k_expand_rows<<<grid2d(w, h), 256, 0, st>>>(g, w, h, nx, out, prof_dev);
     return launched_init("expand_rows");
+}
+
+int launch_push_halo(const PushArgs &p, int narrays, cudaStream_t st)
+{
+    k_push_halo<<<dim3((unsigned)narrays, 2, 1), 256, 0, st>>>(p);
+    return launched_init("push_halo");
+}
+
+int launch_signal(unsigned long long *a, unsigned long long *b, unsigned long long value, cudaStream_t st)
+{
+    k_signal<<<1, 1, 0, st>>>(a, b, value);
+    return launched_init("signal");
 }
 
 int launch_fill8(int w, int h, int pitch, double *dst, double value, cudaStream_t st)

@@ -397,6 +397,16 @@ class DeviceBlock:
         buf = C.create_string_buffer(unique_id, 128)
         check(self.L.swcu_comm_init(self.h, nranks, rank, buf))
 
+    def peer_export(self):
+        """IPC handles of this block's prognostic buffers for the neighbouring ranks (swcu_peer_export)."""
+        buf = C.create_string_buffer(_lib.PEER_BLOB_BYTES)
+        check(self.L.swcu_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, side, blob: bytes):
+        """side 0: the block below (rank-1), 1: the block above (rank+1)."""
+        check(self.L.swcu_peer_attach(self.h, int(side), C.create_string_buffer(blob, _lib.PEER_BLOB_BYTES)))
+
     def halo_exchange(self, name):
         check(self.L.swcu_halo_exchange(self.h, FIELD_ID[name]))
 
@@ -469,6 +479,18 @@ class ShallowWaterModel:
 
     def attach_comm(self, unique_id):
         self.block.comm_init(self.world, self.rank, unique_id)
+
+    def attach_peers(self, all_gather_object):
+        """Halo exchange over peer memory instead of NCCL (ranks on one node).  `all_gather_object(list, obj)`
+        is torch.distributed's (or any equivalent): the blobs travel once, at set-up."""
+        if self.world == 1:
+            return
+        blobs = [None] * self.world
+        all_gather_object(blobs, self.block.peer_export())
+        if self.rank > 0:
+            self.block.peer_attach(0, blobs[self.rank - 1])
+        if self.rank + 1 < self.world:
+            self.block.peer_attach(1, blobs[self.rank + 1])
 
     def expl_shallow_water(self, nsteps=1):
         self.block.step(self.tau, nsteps)

@@ -28,6 +28,7 @@ def main():
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 203
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     balance = len(sys.argv) > 4 and sys.argv[4] == "balance"   # slabs of equal work instead of equal height
+    peer = len(sys.argv) > 4 and sys.argv[4] == "peer"         # halo rows over peer memory instead of NCCL
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -62,19 +63,24 @@ def main():
         m.block.close()
         dist.barrier()
     for mode, tiled in ((MODE_FUSED, 1), (MODE_FUSED, 0), (MODE_REFERENCE, 0)):
-        m = model.ShallowWaterModel(bp, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True,
+        sw = model.SwPar(use_tracers=1 if peer else 0)
+        fields = STATE + (("ff1", "ff1p") if peer else ())
+        m = model.ShallowWaterModel(bp, sw, mask=mask, device=local, mode=mode, rank=rank, world=world, keep_mu=True,
                                     balance=balance, device_init=balance)
         if mode == MODE_FUSED:
             m.block.set_option("tiled", tiled)
-        ids = [model.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        m.attach_comm(ids[0])
+        if peer and mode == MODE_FUSED:
+            m.attach_peers(dist.all_gather_object)
+        else:
+            ids = [model.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            m.attach_comm(ids[0])
         m.step(steps)
         assert m.block.synchronize() == 0
         d = m.dims
         rows = slice(d.ny_start - d.bnd_y1, d.ny_end - d.bnd_y1 + 1)
         parts = {}
-        for f in STATE:
+        for f in fields:
             mine = torch.from_numpy(m.get(f)[rows].copy()).cuda()
             sizes = [None] * world
             dist.all_gather_object(sizes, mine.shape[0])
@@ -82,9 +88,9 @@ def main():
             dist.all_gather(bufs, mine)
             parts[f] = torch.cat(bufs, 0).cpu().numpy()
         if rank == 0:
-            one = model.ShallowWaterModel(bp, mask=mask, device=local, mode=MODE_FUSED, keep_mu=True)
+            one = model.ShallowWaterModel(bp, sw, mask=mask, device=local, mode=MODE_FUSED, keep_mu=True)
             one.step(steps)
-            for f in STATE:
+            for f in fields:
                 ref = one.get(f)[2:-2]
                 same = np.array_equal(parts[f], ref)
                 ok &= same
@@ -92,9 +98,9 @@ def main():
                     print(f"MISMATCH vs 1-GPU mode={mode} tiled={tiled} {f}: max|d|={np.abs(parts[f] - ref).max()}")
             if nx * ny <= 400 * 400:
                 from oracle_lib import OracleModel, make_config
-                o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+                o = OracleModel(make_config(nx, ny, keep_mu=1, use_tracers=1 if peer else 0), mask)
                 o.step(steps)
-                for f in STATE:
+                for f in fields:
                     same = np.array_equal(parts[f], o.get(f)[2:-2])
                     ok &= same
                     if not same:

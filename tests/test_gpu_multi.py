@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("shape", [(150, 203, 40), (77, 64, 25), (150, 203, 40, "balance")],
-                         ids=["150x203", "77x64", "150x203-balanced-slabs"])
+@pytest.mark.parametrize("shape", [(150, 203, 40), (77, 64, 25), (150, 203, 40, "balance"), (150, 203, 40, "peer")],
+                         ids=["150x203", "77x64", "150x203-balanced-slabs", "150x203-peer-memory-halos-tracers"])
 def test_slabs_over_nccl_bitwise(swlib, cuda_device, shape):
     import torch
     n = torch.cuda.device_count()
