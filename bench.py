@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--r-diss", type=float, default=0.0, help="Rayleigh bottom friction 1/s (config 4: 5e-6)")
     ap.add_argument("--tracers", action="store_true", help="use_tracers = 1 (config 5)")
     ap.add_argument("--cartesian", action="store_true", help="curve_grid = 0")
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU halo exchange: ncclSend/Recv, or stores into the neighbours' memory over NVLink "
+                         "(CUDA IPC, FUSED mode); auto = peer memory when every rank can map its neighbours, else NCCL")
     ap.add_argument("--balance", action="store_true",
                     help="y-slabs of equal work (all-land tiles are nearly free) instead of equal height")
     args = ap.parse_args()
@@ -242,7 +245,17 @@ def main():
                                 r_diss=args.r_diss, stripe_rows=1024 if nx * (ny // world) > 3000 * 3000 else None,
                                 device_init=not args.host_init, balance=args.balance)
     t_setup = time.perf_counter() - t_setup
-    if world > 1:
+    halo = "nccl"
+    if world > 1 and args.halo in ("auto", "peer") and mode == MODE_FUSED:
+        from ocean_model_arch_b200._lib import SwcuError
+        try:
+            m.attach_peers(dist.all_gather_object)
+            halo = "peer"
+        except SwcuError:
+            if args.halo == "peer":
+                raise
+    args.halo_used = halo
+    if world > 1 and halo == "nccl":
         ids = [model.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         m.attach_comm(ids[0])
@@ -442,6 +455,9 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "device_bytes": blk.device_bytes,
+                "halo": None if world == 1 else (
+                    "boundary rows stored into the neighbours' memory over NVLink (CUDA IPC), streams wait on step "
+                    "counters; no NCCL in the step" if args.halo_used == "peer" else "ncclSend/ncclRecv on a side stream"),
                 "setup": {"seconds": t_setup, "inputs": "host arrays uploaded" if args.host_init else
                           "masks/metrics built on the device, Gaussian state from the host"}}
         print(json.dumps(line), flush=True)

@@ -314,6 +314,7 @@ int swcu_halo_exchange(swcu_ctx *ctx, int field);
 #define SWCU_PEER_BLOB_BYTES 2048
 int swcu_peer_export(swcu_ctx *ctx, void *blob);
 int swcu_peer_attach(swcu_ctx *ctx, int side, const void *blob);
+int swcu_peer_detach(swcu_ctx *ctx); /* unmaps both sides (all ranks call it before re-attaching) */
 
 /* Several blocks per process (parallel.par bppnx x bppny > 1 x 1, and the reference's _GPU_MULTI_
  * one-process-many-GPUs mode): swcu_link ties two contexts of the same process that are neighbours

@@ -115,6 +115,7 @@ _SIGNATURES = {
     "swcu_copy_field": [_P, _I, _I],
     "swcu_peer_export": [_P, _P],
     "swcu_peer_attach": [_P, _I, _P],
+    "swcu_peer_detach": [_P],
     "swcu_link": [_P, _P],
     "swcu_unlink": [_P],
     "swcu_step_group": [C.POINTER(_P), _I, _D, _I],

@@ -1537,6 +1537,19 @@ int swcu_peer_export(swcu_ctx *c, void *blob)
     return SWCU_OK;
 }
 
+int swcu_peer_detach(swcu_ctx *c)
+{
+    if (!c) return SWCU_OK;
+    Use use(c->device);
+    cudaDeviceSynchronize();
+    for (auto &pl : c->peer) {
+        for (void *p : pl.opened) cudaIpcCloseMemHandle(p);
+        pl = swcu_ctx::PeerLink();
+    }
+    if (c->flags) SWCU_CUDA(cudaMemset(c->flags, 0, 8 * sizeof(unsigned long long)));
+    return SWCU_OK;
+}
+
 int swcu_peer_attach(swcu_ctx *c, int side, const void *blob)
 {
     if (!c || !blob || (side != 0 && side != 1)) { set_error("bad argument"); return SWCU_ERR_ARG; }

@@ -486,11 +486,28 @@ class ShallowWaterModel:
         if self.world == 1:
             return
         blobs = [None] * self.world
-        all_gather_object(blobs, self.block.peer_export())
-        if self.rank > 0:
-            self.block.peer_attach(0, blobs[self.rank - 1])
-        if self.rank + 1 < self.world:
-            self.block.peer_attach(1, blobs[self.rank + 1])
+        try:
+            mine = self.block.peer_export()
+        except _lib.SwcuError as e:
+            mine = e
+        all_gather_object(blobs, mine)
+        ok, err = True, None
+        try:
+            for b in blobs:
+                if isinstance(b, Exception):
+                    raise b
+            if self.rank > 0:
+                self.block.peer_attach(0, blobs[self.rank - 1])
+            if self.rank + 1 < self.world:
+                self.block.peer_attach(1, blobs[self.rank + 1])
+        except _lib.SwcuError as e:
+            ok, err = False, e
+        # every rank must end up on the same path: all attached, or none
+        oks = [None] * self.world
+        all_gather_object(oks, ok)
+        if not all(oks):
+            check(self.block.L.swcu_peer_detach(self.block.h))
+            raise _lib.SwcuError(4, f"peer-memory halo path unavailable on some rank ({err})")
 
     def expl_shallow_water(self, nsteps=1):
         self.block.step(self.tau, nsteps)
