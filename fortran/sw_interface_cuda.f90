@@ -21,6 +21,7 @@ module swcuda_c_binding
 
     integer(c_int), parameter :: SWCU_OK = 0
     integer(c_int), parameter :: SWCU_MODE_REFERENCE = 0, SWCU_MODE_FUSED = 1
+    integer, parameter :: SWCU_PEER_BLOB_BYTES = 2048
 
     ! enum swcu_field (include/swcuda.h)
     integer(c_int), parameter :: SWCU_F_SSH = 0, SWCU_F_SSHN = 1, SWCU_F_SSHP = 2,                &
@@ -113,6 +114,19 @@ module swcuda_c_binding
             type(c_ptr), value :: ctx
             real(c_double), value :: tau
             integer(c_int), value :: nsteps
+            integer(c_int) :: rc
+        end function
+        function swcu_peer_export(ctx, blob) bind(C, name="swcu_peer_export") result(rc)
+            import :: c_ptr, c_char, c_int
+            type(c_ptr), value :: ctx
+            character(kind=c_char), intent(out) :: blob(*)
+            integer(c_int) :: rc
+        end function
+        function swcu_peer_attach(ctx, side, blob) bind(C, name="swcu_peer_attach") result(rc)
+            import :: c_ptr, c_char, c_int
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: side
+            character(kind=c_char), intent(in) :: blob(*)
             integer(c_int) :: rc
         end function
         function swcu_link(a, b) bind(C, name="swcu_link") result(rc)
@@ -241,7 +255,8 @@ contains
         type(swcu_dims) :: d
         type(swcu_params) :: p
         character(kind=c_char) :: id(128)
-        integer :: k, k2, ierr, ndev
+        character(kind=c_char) :: blob_mine(SWCU_PEER_BLOB_BYTES), blob_nbr(SWCU_PEER_BLOB_BYTES)
+        integer :: k, k2, ierr, ndev, node_comm, node_size, side, nbr, to
 
         ndev = max(1, int(swcu_device_count()))
         if (mpp_count > 1 .and. domain%bcount > 1) call abort_model('swcuda: several ranks need one block per rank')
@@ -281,11 +296,29 @@ contains
                 if (blocks_touch(k, k2)) call check(swcu_link(ctx(k), ctx(k2)), 'link')
             enddo
         enddo
-        ! one NCCL communicator over the y-slab ranks; the id travels over the existing MPI communicator
         if (mpp_count > 1) then
-            if (mpp_is_master()) call check(swcu_comm_unique_id(id), 'unique_id')
-            call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
-            call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), id), 'comm_init')
+            call mpi_comm_split_type(mpp_cart_comm, mpi_comm_type_shared, 0, mpi_info_null, node_comm, ierr)
+            call mpi_comm_size(node_comm, node_size, ierr)
+            if (node_size == mpp_count) then
+                ! all ranks on one node: halo rows are stored straight into the neighbours' memory (CUDA IPC),
+                ! the 2048-byte blobs travel once over MPI
+                call check(swcu_peer_export(ctx(1), blob_mine), 'peer_export')
+                do side = 0, 1
+                    nbr = mpp_rank - 1 + 2 * side                       ! side 0: rank-1, side 1: rank+1
+                    to  = mpp_rank + 1 - 2 * side
+                    if (nbr < 0 .or. nbr >= mpp_count) nbr = mpi_proc_null
+                    if (to  < 0 .or. to  >= mpp_count) to  = mpi_proc_null
+                    call mpi_sendrecv(blob_mine, SWCU_PEER_BLOB_BYTES, mpi_character, to,  side,   &
+                                      blob_nbr,  SWCU_PEER_BLOB_BYTES, mpi_character, nbr, side,   &
+                                      mpp_cart_comm, mpi_status_ignore, ierr)
+                    if (nbr /= mpi_proc_null) call check(swcu_peer_attach(ctx(1), int(side, c_int), blob_nbr), 'peer_attach')
+                enddo
+            else
+                ! several nodes: one NCCL communicator over the y-slab ranks; the id travels over MPI
+                if (mpp_is_master()) call check(swcu_comm_unique_id(id), 'unique_id')
+                call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
+                call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), id), 'comm_init')
+            endif
         endif
     end subroutine
 
