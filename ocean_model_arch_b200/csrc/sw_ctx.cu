@@ -8,11 +8,17 @@
 // REFERENCE mode keeps all 32 real(8) + 17 real(4) arrays of ocean_type / grid_type and launches
 // the reference's kernel sequence (control/shallow_water/shallow_water.f90:22-94).
 // FUSED mode keeps the six prognostic arrays twice (ping-pong), hhq_rest, mu, six scratch arrays,
-// ten real(4) arrays and one mask byte per cell, and launches prep + update per step.
+// ten real(4) arrays, per-row metric tables and one mask byte per cell; a step is ONE launch of the
+// TMA-tiled kernel (or prep + update when the metrics vary along x) plus one launch per tracer step.
 //
-// Multi-GPU (y-slabs, one block per GPU): halo rows travel with ncclSend/ncclRecv on a side
-// stream; in FUSED mode the two boundary strips are computed first, their exchange overlaps the
-// interior update (replaces shared/mpp/sync.f90:294-374 + syncborder_block2D_gen_all.fi).
+// Neighbouring blocks, three ways (one per context):
+//   communicator  one block per process and GPU, y-slabs: ncclSend/ncclRecv of halo rows on a side
+//                 stream (replaces shared/mpp/sync.f90:294-374 + syncborder_block2D_gen_all.fi)
+//   peer memory   the same cut for processes on one node: boundary rows are stored straight into the
+//                 neighbours' buffers (CUDA IPC), streams wait on step counters
+//   links         several blocks of ONE process, any bnx x bny cut, one GPU or several: strided
+//                 device-to-device pulls ordered by events (syncborder_block2D_gen_all.fi:218-249)
+// In FUSED mode the two boundary strips are computed first and the exchange overlaps the interior.
 #include <dlfcn.h>
 #include <unistd.h>
 #include <nccl.h>
