@@ -1,4 +1,6 @@
-// sw_kernels_fused.cu -- Level B fused step: the reference's K1..K11 collapsed into two launches.
+// sw_kernels_fused.cu -- Level B fused step: the reference's K1..K11 collapsed into ONE launch
+// (k_step: both stages below on shared-memory tiles staged by TMA; needs the per-row metric tables)
+// or into two launches from global memory (k_prep + k_update; any grid), plus k_tracer.
 //
 //   prep   (A): from the time-level-n state (ssh, u, v, up, vp) and the static fields, the
 //               neighbour-shared intermediates: depths on U/V/H points (K10/K2: depth.f90:57-94),
