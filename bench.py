@@ -335,6 +335,10 @@ def main():
                     "step_bytes_per_cell_launched": bpc if tiled else B_UPDATE + B_PREP,
                     "step_frac_vs_reference_granularity_1196B": B_REF_STEP * (value / world) / 1e9 / peak,
                     "step_frac_vs_floor_196B": B_MIN_STEP * (value / world) / 1e9 / peak}
+            if tiled and os.path.exists(tp):
+                pipes = json.load(open(tp)).get("k_step_pipes", {}).get(str(S))
+                if pipes:   # what actually bounds the fused kernel (from the committed ncu capture, not measured live)
+                    roof["limiting_units_ncu"] = pipes
             if mask is not None and tiled:
                 roof["note"] = "CTAs of all-land 32x8 tiles exit before any load; their cells are still counted here"
             if not tiled:
