@@ -149,6 +149,63 @@ def test_linear_gravity_mode_known_answer():
     assert np.sign(a).min() < 0 < np.sign(a).max()               # it really oscillates
 
 
+def test_inertial_and_viscous_known_answers():
+    """Two more known answers from the PHYSICS, not from the reference's code (carthesian grid, flat
+    bottom, rigid-lid depths, flat ssh, so every other term vanishes at cells away from the walls):
+
+    * f-plane: a uniform current (u0, v0) turns clockwise in the northern hemisphere,
+      du/dt = +f v, dv/dt = -f u.  One leapfrog step from equal time levels must give
+      u = u0 + 2 tau f v0, v = v0 - 2 tau f u0 with f = rlh_s = 2 Omega sin(45 deg) (real(4)).
+      Pins the sign, the 4-point averaging and the hhh*dxb*dyb / (hhu*dxt*dyh) bookkeeping of K7's
+      Coriolis term, and that uniform flow feels no advection (K3, K4).
+    * a shear flow u(y) under lateral viscosity nu diffuses, du/dt = nu d2u/dy2, evaluated at the lagged
+      level like every leapfrog scheme must: u = u0 + 2 tau nu (u0(n+1) - 2 u0(n) + u0(n-1)) / dy^2.
+      Pins K5's shearing stress, K6's dxb^2 * mu * hh * str_s flux difference and the sign of RHS_dif."""
+    nx, ny, tau = 60, 56, 2.0
+    jj, ii = np.mgrid[1:ny + 1, 1:nx + 1]
+    core = (slice(20, 36), slice(20, 40))                      # cells far from the walls
+
+    def model(**kw):
+        m = OracleModel(make_config(nx, ny, curve_grid=0, dxst=0.01, dyst=0.02, full_free_surface=0, time_step=tau,
+                                    time_smooth=0.0, **kw), None)
+        for f in ("ssh", "sshp", "sshn"):
+            m.set(f, np.zeros((ny, nx)))
+        return m
+
+    # ---- inertial turning
+    m = model()
+    u0, v0 = 0.3, -0.2
+    for f, val, mask in (("ubrtr", u0, "lcu"), ("ubrtrp", u0, "lcu"), ("vbrtr", v0, "lcv"), ("vbrtrp", v0, "lcv")):
+        m.set(f, val * m.get(mask).astype(np.float64))
+    f_cor = float(m.get("rlh_s")[30, 30])
+    omega = 7.2921159e-5
+    assert abs(f_cor - 2 * omega * np.sqrt(0.5)) < 1e-10 and f_cor > 0      # northern hemisphere
+    m.step(1)
+    assert np.abs(m.get("ubrtr")[core] - (u0 + 2 * tau * f_cor * v0)).max() < 1e-15
+    assert np.abs(m.get("vbrtr")[core] - (v0 - 2 * tau * f_cor * u0)).max() < 1e-15
+    assert not m.get("ssh")[core].any()                                       # uniform flow: no divergence there
+
+    # ---- viscous decay of a shear flow
+    nu = 500.0
+    m = model(keep_mu=1, lvisc_2=nu)
+    m.set("rlh_s", np.zeros((ny, nx), np.float32))
+    dy = float(m.get("dy")[30, 30])
+    prof = 0.1 * np.sin(2 * np.pi * jj / 17.0) + 0.05 * np.cos(2 * np.pi * jj / 9.0)
+    for f in ("ubrtr", "ubrtrp"):
+        m.set(f, prof * m.get("lcu"))
+    assert np.array_equal(m.get("mu")[core], np.full((16, 20), nu))
+    m.step(1)
+    lap = (np.roll(prof, -1, 0) - 2 * prof + np.roll(prof, 1, 0)) / dy ** 2
+    dx = float(m.get("dx")[30, 30])
+    sq4 = float(np.float32(dx) * np.float32(dx)) / dx ** 2     # K6 squares dxb in REAL(4) (vel_ssh.f90:432)
+    assert abs(sq4 - 1) > 1e-9                                   # ... and the test resolves that
+    want = prof + 2 * tau * nu * lap * sq4
+    got = m.get("ubrtr")
+    assert np.abs(got[core] - want[core]).max() < 1e-9 * np.abs(want[core] - prof[core]).max()
+    assert np.abs(got[core] - prof[core]).max() > 1e-9                        # viscosity did act
+    assert np.abs(m.get("vbrtr")[core]).max() < 1e-18                         # only rounding residue of the metric terms
+
+
 # ---- the C oracle against an independent NumPy restatement written from the Fortran sources -------------
 import np_restatement as npr  # noqa: E402
 
