@@ -206,6 +206,78 @@ def test_inertial_and_viscous_known_answers():
     assert np.abs(m.get("vbrtr")[core]).max() < 1e-18                         # only rounding residue of the metric terms
 
 
+def test_free_surface_mass_flux_known_answer():
+    """full_free_surface = 1: the volume flux through a face is u * (H + ssh averaged onto the face), so in a
+    uniform current u0 the surface elevation is advected, ssh - 2 tau u0 (ssh(m+1) - ssh(m-1)) / (2 dx)
+    (continuity with the depth correction of K10 feeding K1).  The model's own Gaussian bump is the profile."""
+    nx, ny, tau, u0 = 64, 48, 2.0, 0.4
+    m = OracleModel(make_config(nx, ny, curve_grid=0, dxst=0.01, dyst=0.01, time_step=tau), None)
+    m.set("rlh_s", np.zeros((ny, nx), np.float32))
+    for f in ("ubrtr", "ubrtrp"):
+        m.set(f, u0 * m.get("lcu").astype(np.float64))
+    ssh0 = m.get("ssh")
+    dx = float(m.get("dx")[24, 30])
+    core = (slice(12, 36), slice(16, 48))
+    assert np.abs(m.get("hhu")[core] - (100.0 + (ssh0 + np.roll(ssh0, -1, 1)) / 2)[core]).max() < 1e-12
+    m.step(1)
+    inc = -2 * tau * u0 * (np.roll(ssh0, -1, 1) - np.roll(ssh0, 1, 1)) / (2 * dx)
+    got = m.get("ssh") - ssh0
+    assert np.abs(got[core] - inc[core]).max() < 1e-6 * np.abs(inc[core]).max()   # real(4) dx*dy in K1: 6e-8
+    assert np.abs(inc[core]).max() > 1e-6
+
+
+def test_advection_filter_and_tracer_known_answers():
+    """Known answers for the remaining terms, again from the equations (carthesian, flat, rigid-lid depths,
+    no Coriolis; cells far from the walls, one step from equal time levels):
+
+    * momentum self-advection in flux form, u_t = -(u u)_x: u - 2 tau ([u]_e^2 - [u]_w^2)/dx with face
+      averages [u]_e = (u(m) + u(m+1))/2 (K4);
+    * the Robert-Asselin filter: the lagged level becomes u0 + (time_smooth/2)(u_new - 2 u0 + u0) (K8);
+    * a tracer in a uniform current with diffusivity K = mu: centred advection plus diffusion,
+      f - 2 tau u0 (f(m+1) - f(m-1))/(2 dx) + 2 tau K (f(m+1) - 2 f(m) + f(m-1))/dx^2 (tracer kernels)."""
+    nx, ny, tau, ts = 64, 48, 2.0, 0.5
+    jj, ii = np.mgrid[1:ny + 1, 1:nx + 1]
+    core = (slice(16, 32), slice(20, 44))
+    m = OracleModel(make_config(nx, ny, curve_grid=0, dxst=0.01, dyst=0.01, full_free_surface=0, time_step=tau,
+                                time_smooth=ts, ksw_lat=0), None)
+    m.set("rlh_s", np.zeros((ny, nx), np.float32))
+    for f in ("ssh", "sshp", "sshn"):
+        m.set(f, np.zeros((ny, nx)))
+    dx = float(m.get("dx")[24, 30])
+    prof = 0.2 + 0.05 * np.sin(2 * np.pi * ii / 13.0)
+    for f in ("ubrtr", "ubrtrp"):
+        m.set(f, prof * m.get("lcu"))
+    m.step(1)
+    ue, uw = (prof + np.roll(prof, -1, 1)) / 2, (prof + np.roll(prof, 1, 1)) / 2
+    want = prof - 2 * tau * (ue ** 2 - uw ** 2) / dx
+    got = m.get("ubrtr")
+    assert np.abs(got[core] - want[core]).max() < 1e-9 * np.abs(want[core] - prof[core]).max()
+    assert np.abs(want[core] - prof[core]).max() > 1e-7
+    want_p = prof + ts * (want - 2 * prof + prof) / 2                   # Robert-Asselin, coefficient time_smooth/2
+    assert np.abs(m.get("ubrtrp")[core] - want_p[core]).max() < 1e-9 * np.abs(want_p[core] - prof[core]).max()
+    assert np.abs(m.get("vbrtr")[core]).max() < 1e-18
+
+    K, u0 = 300.0, 0.25
+    m = OracleModel(make_config(nx, ny, curve_grid=0, dxst=0.01, dyst=0.01, full_free_surface=0, time_step=tau,
+                                time_smooth=ts, use_tracers=1, keep_mu=1, lvisc_2=K), None)
+    m.set("rlh_s", np.zeros((ny, nx), np.float32))
+    for f in ("ssh", "sshp", "sshn"):
+        m.set(f, np.zeros((ny, nx)))
+    for f in ("ubrtr", "ubrtrp"):
+        m.set(f, u0 * m.get("lcu").astype(np.float64))
+    tr = 1.0 + 0.3 * np.cos(2 * np.pi * ii / 11.0) * m.get("lu")
+    for f in ("ff1", "ff1p", "ff1n"):
+        m.set(f, tr)
+    m.step(1)
+    assert np.abs(m.get("ubrtr")[core] - u0).max() < 1e-15               # uniform current: nothing acts on it
+    adv = -u0 * (np.roll(tr, -1, 1) - np.roll(tr, 1, 1)) / (2 * dx)
+    dif = K * (np.roll(tr, -1, 1) - 2 * tr + np.roll(tr, 1, 1)) / dx ** 2
+    want = tr + 2 * tau * (adv + dif)
+    got = m.get("ff1")
+    assert np.abs(got[core] - want[core]).max() < 1e-9 * np.abs(want[core] - tr[core]).max()
+    assert np.abs(2 * tau * adv[core]).max() > 1e-6 and np.abs(2 * tau * dif[core]).max() > 1e-6
+
+
 # ---- the C oracle against an independent NumPy restatement written from the Fortran sources -------------
 import np_restatement as npr  # noqa: E402
 
