@@ -11,6 +11,10 @@
  * real(4)/real(8) promotion rules, evaluated strictly (no FMA contraction, no reassociation:
  * build with -ffp-contract=off -fno-fast-math).  Every function cites the reference file:line
  * it follows (paths relative to /root/reference).
+ * What stands in for the missing pins (tests/test_oracle.py): committed digests, an independent
+ * NumPy restatement written from the Fortran (tests/np_restatement.py) that must agree bitwise on
+ * every array, analytic known answers for every term of the scheme, and the invariants of
+ * SURVEY.md 8c (decomposition invariance, conservation, untouched land).
  */
 #ifndef SW_ORACLE_H
 #define SW_ORACLE_H
