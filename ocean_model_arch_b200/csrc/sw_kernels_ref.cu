@@ -57,7 +57,10 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_ssh(Geo g, MetRow mr, doub
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(lu[c])) sshn[c] = f_sshn(c, r, p, tau, mt, hhu, hhv, sshp, u, v);
+    // evaluate first, store under the mask: the operand loads then do not wait for the mask load
+    // (masked-out lanes may compute Inf/NaN from zero metrics; they are never stored)
+    const double val = f_sshn(c, r, p, tau, mt, hhu, hhv, sshp, u, v);
+    if (on(lu[c])) sshn[c] = val;
 }
 
 // K7 -- kernel/shallow_water/vel_ssh.f90:163-193
@@ -80,12 +83,12 @@ __global__ void __launch_bounds__(BX *BY) k_sw_update_uv(Geo g, MetRow mr, Tau t
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, dxt, dyt, dxh, dyh, dxb, dyb, rlh_s};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(lcu[c]))
-        un[c] = f_un(c, r, p, tt, mt, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
-                     (double)(rdis[c] + rdis[c + 1]), hhh, ssh, v, up);
-    if (on(lcv[c]))
-        vn[c] = f_vn(c, r, p, tt, mt, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
-                     (double)(rdis[c] + rdis[c + p]), hhh, ssh, u, vp);
+    const double nu = f_un(c, r, p, tt, mt, hhu[c], hhun[c], hhup[c], RHSx[c], RHSx_dif[c], RHSx_adv[c],
+                           (double)(rdis[c] + rdis[c + 1]), hhh, ssh, v, up);
+    const double nv = f_vn(c, r, p, tt, mt, hhv[c], hhvn[c], hhvp[c], RHSy[c], RHSy_dif[c], RHSy_adv[c],
+                           (double)(rdis[c] + rdis[c + p]), hhh, ssh, u, vp);
+    if (on(lcu[c])) un[c] = nu;
+    if (on(lcv[c])) vn[c] = nv;
 }
 
 // K8 -- kernel/shallow_water/vel_ssh.f90:226-243 (range grown by one cell)
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(BX *BY) k_uv_trans_vort(Geo g, MetRow mr, cons
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, dxt, dyt, nullptr, nullptr, dxb, dyb, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(luu[c])) vort[c] = f_vort(c, r, p, mt, u, v);
+    const double val = f_vort(c, r, p, mt, u, v);
+    if (on(luu[c])) vort[c] = val;
 }
 
 // K4 -- kernel/shallow_water/vel_ssh.f90:318-371
@@ -135,8 +139,10 @@ __global__ void __launch_bounds__(BX *BY) k_uv_trans(Geo g, MetRow mr,
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{nullptr, nullptr, nullptr, nullptr, dxh, dyh, nullptr, nullptr, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(lcu[c])) RHSx[c] = f_rhsx_adv(c, r, p, mt, (double)luu[c], (double)luu[c - p], u, v, vort, hu, hv, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh);
+    const double rx = f_rhsx_adv(c, r, p, mt, (double)luu[c], (double)luu[c - p], u, v, vort, hu, hv, hh);
+    const double ry = f_rhsy_adv(c, r, p, mt, u, v, vort, hu, hv, hh);
+    if (on(lcu[c])) RHSx[c] = rx;
+    if (on(lcv[c])) RHSy[c] = ry;
 }
 
 // K6 -- kernel/shallow_water/vel_ssh.f90:414-450
@@ -154,8 +160,10 @@ __global__ void __launch_bounds__(BX *BY) k_uv_diff2(Geo g, MetRow mr,
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(lcu[c])) RHSx[c] = f_rhsx_dif(c, r, p, mt, hq[c], hq[c + 1], mu, str_t, str_s, hh);
-    if (on(lcv[c])) RHSy[c] = f_rhsy_dif(c, r, p, mt, hq[c], hq[c + p], mu, str_t, str_s, hh);
+    const double rx = f_rhsx_dif(c, r, p, mt, hq[c], hq[c + 1], mu, str_t, str_s, hh);
+    const double ry = f_rhsy_dif(c, r, p, mt, hq[c], hq[c + p], mu, str_t, str_s, hh);
+    if (on(lcu[c])) RHSx[c] = rx;
+    if (on(lcv[c])) RHSy[c] = ry;
 }
 
 // K5 -- kernel/shallow_water/mixing.f90:38-56
@@ -172,8 +180,9 @@ __global__ void __launch_bounds__(BX *BY) k_stress_components(Geo g, MetRow mr,
     SWCU_CELL(g.nx_start, g.ny_start, g.nx_end, g.ny_end);
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
-    if (on(lu[c])) str_t[c] = f_str_t(c, r, p, mt, u, v);
-    if (on(luu[c])) str_s[c] = f_str_s(c, r, p, mt, u, v);
+    const double st = f_str_t(c, r, p, mt, u, v), ss = f_str_s(c, r, p, mt, u, v);
+    if (on(lu[c])) str_t[c] = st;
+    if (on(luu[c])) str_s[c] = ss;
 }
 
 // the three interpolations of hh_init / hh_update for one source depth (depth.f90:57-94);
@@ -221,8 +230,7 @@ __global__ void __launch_bounds__(BX *BY) k_hh_init(Geo g, MetRow mr, double ffs
     hq[c] = q; hqp[c] = qp; hqn[c] = qn;  // whole-array statements, depth.f90:48-50
     if (m < g.nx_start - 1 || m > g.nx_end || n < g.ny_start - 1 || n > g.ny_end) return;
     const long e = c + 1, no = c + p, en = c + 1 + p;
-    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
-    if (!(wu || wv || wh)) return;
+    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);   // used for the stores only
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
     const Interp3 i0 = interp3(q, h_r[e] + sh[e] * ffs, h_r[no] + sh[no] * ffs, h_r[en] + sh[en] * ffs, c, r, p, lu, mt);
@@ -250,8 +258,7 @@ __global__ void __launch_bounds__(BX *BY) k_hh_update(Geo g, MetRow mr,
     hqn[c] = qn;  // depth.f90:129
     if (m < g.nx_start - 1 || m > g.nx_end || n < g.ny_start - 1 || n > g.ny_end) return;
     const long e = c + 1, no = c + p, en = c + 1 + p;
-    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);
-    if (!(wu || wv || wh)) return;
+    const bool wu = on(llu[c]), wv = on(llv[c]), wh = on(luh[c]);   // used for the stores only
     const MetGen mg{dx, dy, dxt, dyt, dxh, dyh, dxb, dyb, nullptr};
     const auto &mt = Pick<ROW>::get(mg, mr);
     const Interp3 in = interp3(qn, h_r[e] + sh[e], h_r[no] + sh[no], h_r[en] + sh[en], c, r, p, lu, mt);
