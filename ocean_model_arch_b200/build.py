@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswcuda.so")
-SOURCES = ["sw_api_level_a.cu", "sw_kernels_ref.cu", "sw_kernels_fused.cu", "sw_init.cu", "sw_ctx.cu", "sw_host.cpp"]
-HEADERS = ["sw_common.h", "sw_formulas.cuh", "sw_fused.h", os.path.join("..", "..", "include", "swcuda.h")]
+SOURCES = ["sw_api_level_a.cu", "sw_kernels_ref.cu", "sw_kernels_fused.cu", "sw_kernels_march.cu", "sw_init.cu", "sw_ctx.cu", "sw_host.cpp"]
+HEADERS = ["sw_common.h", "sw_formulas.cuh", "sw_cells.cuh", "sw_fast.cuh", "sw_tables.h", "sw_fused.h", os.path.join("..", "..", "include", "swcuda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -29,6 +29,7 @@
 #include <map>
 #include <vector>
 
+#include "sw_fast.cuh"
 #include "sw_fused.h"
 
 using namespace swcu;
@@ -190,6 +191,15 @@ struct swcu_ctx {
     int tile_land_n0 = 0, tile_land_n1 = -1;  // row range of the launch the flags describe
     bool want_tiled = true;                   // one-launch TMA-tiled step when the tables are usable
     int tile_variant = 4;
+    // tolerance mode (sw_fast.cuh / k_march): "exact" = 0.  The coefficient table depends on tau.
+    bool exact = false;
+    double *fc = nullptr;
+    double fc_tau = 0.0;
+    bool fc_valid = false;
+    int march_warps = 0;                      // SMs x resident warps of k_march on this device
+    MarchPlan plan_main = {0, -1, 0, 0, 0, nullptr};
+    unsigned char *band_land = nullptr;
+    size_t band_land_cap = 0;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
     // per-launch event pairs, filled only inside swcu_profile_steps
     bool prof = false;
@@ -439,6 +449,7 @@ int prepare_metrics(swcu_ctx *c)
 {
     c->metrics_dirty = false;
     c->use_tables = false;
+    c->fc_valid = false;
     if (!c->want_tables) return SWCU_OK;
     FusedArgs a;
     fill_static_args(c, a);
@@ -550,6 +561,15 @@ int fused_main(swcu_ctx *c, double tau)
     a.vort = c->f8[SWCU_F_VORT]; a.str_t = c->f8[SWCU_F_STR_T]; a.str_s = c->f8[SWCU_F_STR_S];
     fill_static_args(c, a);
     a.tab = c->use_tables ? c->tab : nullptr; a.tab_h = c->h;
+    a.fc = nullptr;
+    if (!c->exact && c->use_tables) {  // tolerance mode: per-row coefficients (they contain tau)
+        if (!c->fc) RC(dev_alloc(c, (void **)&c->fc, ((size_t)c->h + 4) * swf::FC_STRIDE * sizeof(double)));
+        if (!c->fc_valid || c->fc_tau != tau) {
+            RC(launch_build_fast(c->tab, c->h, tau, c->fc, c->st));
+            c->fc_valid = true; c->fc_tau = tau; c->launches++;
+        }
+        a.fc = c->fc;
+    }
     {   // x/tau == x*(1/tau) bitwise when tau is a power of two (exact scaling)
         int ex = 0;
         const double mant = frexp(tau, &ex);
@@ -564,7 +584,9 @@ int fused_main(swcu_ctx *c, double tau)
     }
 
     const int ns = g.ny_start, ne = g.ny_end;
-    const bool tiled = c->use_tables && c->want_tiled && step_tiled_supported(g, a);
+    const bool march = a.fc != nullptr && march_supported(g, a);
+    if (march && !c->march_warps) c->march_warps = march_resident_warps(c->device);
+    const bool tiled = !march && c->use_tables && c->want_tiled && step_tiled_supported(g, a);
     // rows of the main launch: everything, or the interior between the two boundary strips
     // neighbours in other processes: over NCCL (communicator) or over peer memory (swcu_peer_attach)
     const bool peers = c->peer[0].on || c->peer[1].on;
@@ -573,6 +595,19 @@ int fused_main(swcu_ctx *c, double tau)
     int main0 = ns, main1 = ne;
     if (lo) main0 = (ns + 1 < ne ? ns + 1 : ne) + 1;
     if (hi && main0 <= ne) main1 = (ne - 1 > main0 ? ne - 1 : main0) - 1;
+    if (march && (c->masks_dirty || c->plan_main.n0 != main0 || c->plan_main.n1 != main1)) {
+        // geometry of the main launch and the all-land flags of its bands
+        march_plan(g, main0, main1, c->march_warps, &c->plan_main);
+        const size_t need = (size_t)(c->plan_main.nwarps > 0 ? c->plan_main.nwarps : 1);
+        if (need > c->band_land_cap) {
+            if (c->band_land) { cudaFree(c->band_land); c->bytes -= (long)c->band_land_cap; }
+            c->band_land = nullptr; c->band_land_cap = 0;
+            RC(dev_alloc(c, (void **)&c->band_land, need));
+            c->band_land_cap = need;
+        }
+        if (main1 >= main0) RC(launch_band_land(g, c->mask, c->plan_main, c->band_land, c->st));
+        c->masks_dirty = false;
+    }
     if (tiled && (c->masks_dirty || c->tile_land_n0 != main0 || c->tile_land_n1 != main1)) {
         // (re)build the all-land tile flags of the main launch
         int ntx = 0, nty = 0;
@@ -591,7 +626,7 @@ int fused_main(swcu_ctx *c, double tau)
     if (tiled) {
         const double *src[8] = {a.ssh, a.sshp, a.u, a.up, a.v, a.vp, a.h_r, a.mu};
         for (int k = 0; k < 8; ++k) RC(tensor_map_for(c, src[k], &maps.m[k]));
-    } else {
+    } else if (!march) {
         PROF(0, launch_prep(g, a, ns - 1, ne + 1, c->st));
         c->launches++;
     }
@@ -601,7 +636,18 @@ int fused_main(swcu_ctx *c, double tau)
         // the flags describe the tile grid of the main launch only; the boundary strips do not use them
         a.tile_land = (tiled && c->want_land_skip && r0 == main0 && r1 == main1) ? c->tile_land : nullptr;
         RC(prof_mark(c, 1, true, st));
-        RC(tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, st) : launch_update(g, a, r0, r1, st));
+        if (march) {
+            MarchPlan pl;
+            if (r0 == main0 && r1 == main1) {
+                pl = c->plan_main;
+                pl.band_land = c->want_land_skip ? c->band_land : nullptr;
+            } else {
+                march_plan(g, r0, r1, c->march_warps, &pl);  // boundary strip: a few rows, no flags
+            }
+            RC(launch_march(g, a, pl, st));
+        } else {
+            RC(tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, st) : launch_update(g, a, r0, r1, st));
+        }
         RC(prof_mark(c, 1, false, st));
         c->launches++;
         return SWCU_OK;
@@ -981,6 +1027,7 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
     c->pitch = (c->w + 15) / 16 * 16;
     c->plane = (size_t)c->pitch * c->h;
     c->g = make_geo(*dims, c->pitch);
+    if (const char *e = getenv("SWCU_EXACT")) c->exact = atoi(e) != 0;  // default arithmetic of new contexts
     int rc = SWCU_OK;
 #define TRY(call) do { if (!rc) rc = (call); } while (0)
 #define TRYCUDA(call) do { if (!rc) { cudaError_t e__ = (call); if (e__ != cudaSuccess) rc = cuda_fail(e__, #call); } } while (0)
@@ -1043,6 +1090,7 @@ int swcu_destroy(swcu_ctx *c)
     for (auto &p : c->alt) cudaFree(p);
     for (auto &p : c->alt_ff) cudaFree(p);
     cudaFree(c->mask); cudaFree(c->bad_dev);
+    cudaFree(c->fc); cudaFree(c->band_land);
     cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev); cudaFree(c->tile_land);
     if (c->bad_host) cudaFreeHost(c->bad_host);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);
@@ -1100,8 +1148,13 @@ int swcu_set_option(swcu_ctx *c, const char *name, int value)
     if (!c || !name) { set_error("null argument"); return SWCU_ERR_ARG; }
     if (!strcmp(name, "metric_tables")) { c->want_tables = value != 0; c->metrics_dirty = true; return SWCU_OK; }
     if (!strcmp(name, "tiled")) { c->want_tiled = value != 0; return SWCU_OK; }
-    if (!strcmp(name, "tile_variant")) { c->tile_variant = value; c->tmaps.clear(); c->masks_dirty = true; return SWCU_OK; }
+    if (!strcmp(name, "tile_variant")) {
+        if (value < 1 || value > 5) { set_error("tile_variant must be 1..5"); return SWCU_ERR_ARG; }
+        c->tile_variant = value; c->tmaps.clear(); c->masks_dirty = true;
+        return SWCU_OK;
+    }
     if (!strcmp(name, "land_skip")) { c->want_land_skip = value != 0; return SWCU_OK; }
+    if (!strcmp(name, "exact")) { c->exact = value != 0; c->plan_main.n1 = c->plan_main.n0 - 1; c->masks_dirty = true; return SWCU_OK; }
     set_error("unknown option %s", name);
     return SWCU_ERR_ARG;
 }

@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "sw_tables.h"
+
 namespace swcu {
 
 // Geometry of one block array on the device: element (m,n) at base[(n-by1)*pitch + (m-bx1)].
@@ -70,12 +72,7 @@ struct MetGen {
     __device__ __forceinline__ double ryxb(long c, int) const { return (double)(dyb_[c] / dxb_[c]); }  // dyb/dxb
 };
 
-enum MetTab : int {
-    T_DX, T_DY, T_DXT, T_DYT, T_DXH, T_DYH, T_DXB, T_DYB, T_RLH,
-    T_AREA, T_DY2, T_DX2, T_DXB2, T_DYB2, T_RYX, T_RXY, T_RXYB, T_RYXB,
-    // correctly rounded reciprocals (1.0 / value, IEEE division) of the divisors the step uses
-    T_RDXT, T_RDYT, T_RDXH, T_RDYH, T_RDXB, T_RDYB, T_RAREA, T_COUNT
-};
+// (enum MetTab: sw_tables.h, shared with the host-compilable sw_fast.cuh)
 
 struct MetRow {
     static constexpr bool kRecip = true;

@@ -24,6 +24,7 @@ struct FusedArgs {
     const float *rdis;  // nullptr <=> identically zero
     const double *tab;  // per-row metric tables [T_COUNT][tab_h], nullptr <=> use the 2-D real(4) arrays
     int tab_h;
+    const double *fc;   // tolerance mode: per-row coefficient table [tab_h][FC_STRIDE] (sw_fast.cuh), else nullptr
     const unsigned char *mask;
     // one byte per tile of the main (interior / full-range) tiled launch: 1 <=> every output cell of the tile is land, so
     // the tile is skipped (land cells never change; both ping-pong buffers already hold them).
@@ -38,6 +39,20 @@ struct FusedArgs {
     const double *ff, *ffp;
     double *ff_o, *ffp_o;
 };
+
+// Geometry of one k_march launch (sw_kernels_march.cu): warp w works on warp column w % ncol (28 output
+// columns) and on band w / ncol of the rows [n0..n1] (bands of equal height, +-1 row).
+struct MarchPlan {
+    int n0, n1;
+    int ncol, nbands, nwarps;
+    const unsigned char *band_land;  // [nwarps]: 1 <=> the warp's output cells are all land (skipped), or nullptr
+};
+bool march_supported(const Geo &g, const FusedArgs &a);
+void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl);
+int march_resident_warps(int device);  // SMs x resident warps of k_march: the size of one full wave
+int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st);
+int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st);
+int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st);
 
 // prep on rows [n0..n1] (columns nx_start-1 .. nx_end+1); update on rows [n0..n1] (columns of S)
 int launch_prep(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);

@@ -1,0 +1,410 @@
+// sw_kernels_march.cu -- k_march: the whole shallow-water step (K1..K11) in ONE launch in tolerance
+// mode (sw_fast.cuh), built for the HBM roofline of B200 instead of its fp64 pipe.
+//
+// Work decomposition.  A WARP owns 28 output columns (its 32 lanes carry a 2-column halo on each
+// side) and marches up a band of rows, one row per iteration.  There is no CTA-wide barrier and no
+// shared-memory tile of intermediates:
+//   - the eight input arrays (ssh, sshp, u, up, v, vp, hhq_rest, mu) arrive through a per-warp ring of
+//     RING rows in shared memory, filled with 16-byte cp.async (LDGSTS, zero-filled outside the array)
+//     RING-3 rows ahead of their use: all of a warp's HBM reads are in flight while it computes;
+//   - every input value is read from the ring ONCE when it enters the 3-row stencil window and then
+//     rotates through registers (row b+2 -> b+1 -> b);
+//   - stage A (depths, volume fluxes, stresses, vorticity: the quantities a U/V/H/T point owns) is
+//     evaluated one row ahead of stage B; its results rotate through registers the same way and reach
+//     the east / west neighbours by warp shuffles;
+//   - per-row coefficients come from a 256-byte table row (uniform 16-byte loads through L1).
+// Per cell this costs ~140 fp64 instructions, ~13 shared-memory loads and ~23 shuffles, against ~490
+// fp64 instructions and ~160 shared-memory accesses of the bitwise kernel k_step.
+//
+// Launch geometry: ncol = ceil(columns / 28) warp columns x nbands bands of rows, nbands chosen so
+// that all warps are resident at once (one wave, equal work).  Boundary strips of a multi-GPU step
+// are the same kernel on 2 rows.
+#include "sw_fast.cuh"
+#include "sw_fused.h"
+
+namespace swcu {
+
+namespace {
+
+constexpr int MW = 4;      // warps per CTA (the CTA is only a container: warps never synchronise with each other)
+constexpr int WOUT = 28;   // output columns per warp
+constexpr int NARR = 8;    // staged input arrays
+constexpr int RING = 8;    // rows in the per-warp ring
+constexpr int MARCH_MINB = 2;  // CTAs per SM the register budget is sized for
+constexpr int PADW = 2;    // doubles of padding at both ends of a warp's ring (lane -1 / lane 32 reads)
+constexpr int RING_DOUBLES = RING * NARR * 32 + 2 * PADW;
+constexpr size_t MARCH_SMEM = (size_t)MW * RING_DOUBLES * sizeof(double);
+
+enum { A_SSH, A_SSHP, A_U, A_UP, A_V, A_VP, A_H, A_MU };
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp16(unsigned dst, const void *src, bool valid)
+{
+    const unsigned sz = valid ? 16u : 0u;  // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 64-bit shuffles as two 32-bit ones on the unpacked halves
+__device__ __forceinline__ double shfl_dn(double x)
+{
+    double y;
+    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; shfl.sync.down.b32 lo, lo, 1, 0x1f, 0xffffffff; "
+                 "shfl.sync.down.b32 hi, hi, 1, 0x1f, 0xffffffff; mov.b64 %0, {lo, hi}; }" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double shfl_up(double x)
+{
+    double y;
+    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; shfl.sync.up.b32 lo, lo, 1, 0x0, 0xffffffff; "
+                 "shfl.sync.up.b32 hi, hi, 1, 0x0, 0xffffffff; mov.b64 %0, {lo, hi}; }" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// predicated (never branching) store
+__device__ __forceinline__ void st_if(bool pred, double *ptr, double v)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(ptr), "d"(v) : "memory");
+}
+
+struct MarchIn {
+    const double *in[NARR];  // ssh sshp u up v vp hhq_rest mu
+};
+
+template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS>
+__global__ void __launch_bounds__(MW * 32, MARCH_MINB)
+k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
+{
+    using namespace swf;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wid = blockIdx.x * MW + wib;
+    if (wid >= pl.nwarps) return;
+    const int band = wid / pl.ncol, col = wid - band * pl.ncol;
+    const int nrows = pl.n1 - pl.n0 + 1;
+    const int bs = pl.n0 + (int)((long)band * nrows / pl.nbands);
+    const int be = pl.n0 + (int)((long)(band + 1) * nrows / pl.nbands) - 1;
+    if (be < bs) return;
+    if (pl.band_land && pl.band_land[wid]) return;  // every output cell of this warp's band is land
+
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * RING_DOUBLES + PADW;
+    const unsigned ring_s = smem_addr(ring);
+    const int p = g.pitch, h = g.by2 - g.by1 + 1;
+    const int ax = g.nx_start - 2 - g.bx1 + WOUT * col;  // array column of lane 0
+    const int ac = ax + lane;                            // my array column
+    const int r_first = bs - 2 - g.by1;                  // array row of the first staged row (>= 0)
+    const int r_last = be + 2 - g.by1;                   // last row anybody reads (<= h-1)
+
+    // ---- ring fill: one array row = 16 chunks of 16 B; a warp instruction moves two arrays' rows
+    const int chunk = lane & 15, half = lane >> 4;
+    const int ccol = ax + 2 * chunk;
+    const bool col_ok = ccol + 1 < p;
+    auto issue_row = [&](int r, int slot) {  // r: array row
+        const bool ok = col_ok && r >= 0 && r <= r_last && r < h;
+        const long off = ok ? (long)r * p + ccol : 0;
+#pragma unroll
+        for (int i = 0; i < NARR / 2; ++i) {
+            const double *base = half ? src.in[2 * i + 1] : src.in[2 * i];
+            cp16(ring_s + (unsigned)(((slot * NARR + 2 * i + half) * 32 + 2 * chunk) * sizeof(double)), base + off, ok);
+        }
+        cp_commit();
+    };
+    auto mask_at = [&](int r) -> unsigned {  // mask byte of (r, ac), 0 outside the plane
+        return (r >= 0 && r < h && ac < p) ? (unsigned)__ldg(a.mask + (long)r * p + ac) : 0u;
+    };
+#define RNG(slot, arr, dl) ring[((slot) * NARR + (arr)) * 32 + lane + (dl)]
+
+#pragma unroll
+    for (int j = 0; j < RING; ++j) issue_row(r_first + j, j);
+
+    // ---- state.  Raw inputs are re-read from the ring where they are needed (rows b .. b+2 stay there for the
+    // whole iteration); only COMPUTED values live across iterations.  They sit in two banks that swap roles
+    // every row (the loop is unrolled by two), so nothing is copied from register to register:
+    // in the iteration that outputs row b, bank X holds row b's values and bank Y receives row b+1's.
+    struct Bank {
+        AOut A;            // stage A of the bank's row
+        double q, qm, s;   // thickness at T points of the row ABOVE the bank's row: unmasked, masked, qm_c + qm_e
+        double qpm, sp;    // lagged masked thickness of the bank's row and qpm_c + qpm_e
+        double fyp, fypy;  // northward face fluxes of the row below the bank's row
+    } S[2];
+    S[0].A = AOut{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    S[1].A = S[0].A;
+    S[0].qpm = S[0].sp = S[0].fyp = S[0].fypy = 0.0;
+    S[1].qpm = S[1].sp = S[1].fyp = S[1].fypy = 0.0;
+    unsigned mb0 = 0u, mb1, lue0 = 0u, lue1, mbn;
+    float rd_n = 0.0f;
+
+    // prologue: what stage A of row bs-1 needs from row bs-1 (slot 1)
+    mb1 = mask_at(r_first + 1);
+    mbn = mask_at(r_first + 2);
+    cp_wait<RING - 2>();
+    __syncwarp();
+    {
+        const double h1 = RNG(1, A_H, 0);
+        S[0].q = FFS ? h1 + RNG(1, A_SSH, 0) : h1;
+    }
+    S[0].qm = (mb1 & LU) ? S[0].q : 0.0;
+    S[0].s = S[0].qm + shfl_dn(S[0].qm);
+    S[1].q = S[1].qm = S[1].s = 0.0;
+    lue1 = __shfl_down_sync(0xffffffffu, mb1 & LU, 1);
+
+    const double ts_half = 0.5 * a.ts;
+    const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
+    int s0 = 0, s1i = 1, s2i = 2;  // ring slots of rows b, b+1, b+2
+    const double2 *fc2 = reinterpret_cast<const double2 *>(a.fc);  // a table row = 16 pairs
+
+    auto row = [&](const int b, Bank &X, Bank &Y) {
+        const int rb = b - g.by1;  // array row of b
+        // coefficient rows (uniform addresses, 16-byte loads; pair k = columns 2k, 2k+1 of FastCoef)
+        ACoef ka;
+        BCoef kb;
+        {
+            const double2 *ra = fc2 + (long)(rb + 1) * (FC_STRIDE / 2), *rw = fc2 + (long)rb * (FC_STRIDE / 2);
+            double2 t;
+            t = __ldg(ra + 0); ka.ku = t.x; ka.area = t.y;
+            t = __ldg(ra + 1); ka.area_n = t.x; ka.kv = t.y;
+            t = __ldg(ra + 2); ka.kh = t.x; ka.dyh = t.y;
+            t = __ldg(ra + 3); ka.dxh = t.x; ka.c1 = t.y;
+            t = __ldg(ra + 4); ka.c2 = t.x; ka.c3 = t.y;
+            t = __ldg(ra + 5); ka.cor = t.x; ka.s1 = t.y;
+            t = __ldg(ra + 6); ka.rxy = t.x; ka.rdxh = t.y;
+            t = __ldg(ra + 7); ka.rdxh_s = t.x; ka.rxyb = t.y;
+            t = __ldg(ra + 8); ka.rdxt = t.x; ka.rdxt_n = t.y;
+            t = __ldg(ra + 9); ka.s2 = t.x;
+            t = __ldg(rw + 0); kb.ku = t.x; kb.area = t.y;
+            t = __ldg(rw + 1); kb.area_n = t.x; kb.kv = t.y;
+            t = __ldg(rw + 9); kb.cssh = t.y;
+            t = __ldg(rw + 10); kb.cu = t.x; kb.gx = t.y;
+            t = __ldg(rw + 11); kb.dcx = t.x; kb.dxb2 = t.y;
+            t = __ldg(rw + 12); kb.dxb2_s = t.x; kb.cv = t.y;
+            t = __ldg(rw + 13); kb.gy = t.x; kb.dx2 = t.y;
+            t = __ldg(rw + 14); kb.dx2_n = t.x; kb.dcy = t.y;
+            t = __ldg(rw + 15); kb.rdxt = t.x; kb.rdxh = t.y;
+            kb.tau = a.tau.tau;
+        }
+        const unsigned mb2 = mbn;
+        mbn = mask_at(rb + 3);
+        const double *r0 = ring + s0 * (NARR * 32) + lane, *r1 = ring + s1i * (NARR * 32) + lane,
+                     *r2 = ring + s2i * (NARR * 32) + lane;
+#define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
+
+        // what stage B needs from the row below (bank Y still holds row b-1), before stage A overwrites it
+        const double dvh = X.A.vh - Y.A.vh;
+        const double dss = south_ss(kb, X.A.ss, Y.A.ss);
+        const double zxs = X.A.zx + Y.A.zx;
+        const double fyp_s = X.fyp, fypy_s = X.fypy;
+
+        cp_wait<RING - 3>();  // row b+2 has landed (my copies) ...
+        __syncwarp();         // ... and everybody else's
+
+        // ---- stage A, row b+1 (into bank Y)
+        const double h2 = AT(r2, A_H, 0);
+        const double q2 = FFS ? h2 + AT(r2, A_SSH, 0) : h2;
+        const double qm2 = (mb2 & LU) ? q2 : 0.0;
+        const double s2 = qm2 + shfl_dn(qm2);
+        const unsigned lue2 = __shfl_down_sync(0xffffffffu, mb2 & LU, 1);
+        const double mu1 = AT(r1, A_MU, 0);
+        const double mus = mu1 + AT(r2, A_MU, 0);
+        const double musum = mus + shfl_dn(mus);
+        const int bc1 = (int)(mb1 & LU), bc2 = (int)(mb2 & LU);
+        const double u1 = AT(r1, A_U, 0), v1 = AT(r1, A_V, 0), v_e1 = AT(r1, A_V, 1);
+        const double vp0 = AT(r0, A_VP, 0);
+        Y.A = stage_a<TRANS, LAT>(ka, mb1, bc1 + (int)lue1, bc1 + bc2, bc1 + (int)lue1 + bc2 + (int)lue2, X.q, X.qm, qm2, X.s, s2,
+                                  u1, AT(r2, A_U, 0), v1, v_e1, AT(r1, A_UP, 0), AT(r1, A_UP, -1), AT(r2, A_UP, 0),
+                                  AT(r1, A_VP, 0), vp0, AT(r1, A_VP, 1), mu1, musum);
+        Y.q = q2; Y.qm = qm2; Y.s = s2;
+
+        // ---- stage B, row b
+        const double h1 = AT(r1, A_H, 0);
+        const double qpm1 = (mb1 & LU) ? (FFS ? h1 + AT(r1, A_SSHP, 0) : h1) : 0.0;
+        Y.qpm = qpm1;
+        Y.sp = qpm1 + shfl_dn(qpm1);
+        const double pp = mad(X.qpm, kb.area, qpm1 * kb.area_n);
+        const double uh_w0 = shfl_up(X.A.uh);
+        const double u0 = AT(r0, A_U, 0), v0 = AT(r0, A_V, 0);
+        Flux f = {0.0, 0.0, 0.0, 0.0};
+        double fxp_w = 0.0, fxpy_w = 0.0;
+        if (TRANS) {
+            f = stage_flux((mb0 & LUU) != 0, X.A.uh, shfl_dn(X.A.uh), Y.A.uh, X.A.vh, shfl_dn(X.A.vh), Y.A.vh, u0, AT(r0, A_U, 1),
+                           u1, v0, AT(r0, A_V, 1), v1);
+            fxp_w = shfl_up(f.fxp);
+            fxpy_w = shfl_up(f.fxpy);
+        }
+        Y.fyp = f.fyp; Y.fypy = f.fypy;
+        double t_e0 = 0.0, ss_w0 = 0.0;
+        if (LAT) { t_e0 = shfl_dn(X.A.t); ss_w0 = shfl_up(X.A.ss); }
+        const double zy_w0 = shfl_up(X.A.zy);
+
+        const bool out = lane_out && b >= bs;
+        const long gc = (long)rb * p + ac;
+        double rhsx = 0.0, rhsy = 0.0, rdx = 0.0, rdy = 0.0;
+        if (HAS_RHS && out) { rhsx = a.RHSx[gc]; rhsy = a.RHSy[gc]; }
+        if (HAS_RDISS) {  // vel_ssh.f90:171,185: dble(rdis(m,n) + rdis(m+1,n)), dble(rdis(m,n) + rdis(m,n+1))
+            const float rd_c = rd_n;  // loaded as the row above one iteration ago
+            rd_n = (ac < p && rb + 1 < h) ? __ldg(a.rdis + (long)(rb + 1) * p + ac) : 0.0f;
+            const float rd_e = __shfl_down_sync(0xffffffffu, rd_c, 1);
+            rdx = (double)(rd_c + rd_e);
+            rdy = (double)(rd_c + rd_n);
+        }
+        const int bc0 = (int)(mb0 & LU);
+        const BRaw o = stage_b_raw<TRANS, LAT>(kb, bc0 + (int)lue0, bc0 + bc1, ts_half, AT(r0, A_SSH, 0), AT(r0, A_SSH, 1),
+                                               AT(r1, A_SSH, 0), AT(r0, A_SSHP, 0), X.sp, pp, u0, AT(r0, A_UP, 0), v0, vp0,
+                                               X.A.rhu, X.A.rhv, X.A.uh, uh_w0, dvh, X.A.t, t_e0, Y.A.t, X.A.ss, dss, ss_w0,
+                                               zxs, X.A.zy, zy_w0, f, fxp_w, fyp_s, fxpy_w, fypy_s, rhsx, rhsy, rdx, rdy);
+        // Masked-out cells keep their values, and BOTH ping-pong buffers already hold them (the context copies
+        // the planes once): only the cells the reference's kernels assign are stored (vel_ssh.f90:225-243).
+        const bool sea = out && (mb0 & LU), wu = out && (mb0 & LCU), wv = out && (mb0 & LCV);
+        st_if(sea, a.ssh_o + gc, o.sshn); st_if(sea, a.sshp_o + gc, o.sshpf);
+        st_if(wu, a.u_o + gc, o.un); st_if(wu, a.up_o + gc, o.upf);
+        st_if(wv, a.v_o + gc, o.vn); st_if(wv, a.vp_o + gc, o.vpf);
+        if (sea && ssh_bad(o.sshn)) atomicAdd(a.bad, 1);  // K11
+#undef AT
+
+        // ---- row b leaves the window: refill its ring slot
+        __syncwarp();
+        issue_row(rb + RING, s0);
+        s0 = s1i; s1i = s2i; s2i = s2i + 1 == RING ? 0 : s2i + 1;
+        mb0 = mb1; mb1 = mb2; lue0 = lue1; lue1 = lue2;
+    };
+    for (int b = bs - 2; b <= be; b += 2) {
+        row(b, S[0], S[1]);
+        if (b + 1 <= be) row(b + 1, S[1], S[0]);
+    }
+    cp_wait<0>();
+#undef RNG
+}
+
+inline int launched(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
+}
+
+template <bool T, bool L, bool F, bool R, bool D>
+int march_launch(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+{
+    static unsigned long long attr_set = 0;  // per device opt-in for > 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k_march<T, L, F, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_march)");
+        __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
+    }
+    const unsigned grid = (unsigned)((pl.nwarps + MW - 1) / MW);
+    k_march<T, L, F, R, D><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    return launched("k_march");
+}
+
+template <bool T, bool L, bool F>
+int march_dispatch2(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+{
+    const bool r = a.RHSx != nullptr, d = a.rdis != nullptr;
+    if (r && d) return march_launch<T, L, F, true, true>(g, a, src, pl, st);
+    if (r) return march_launch<T, L, F, true, false>(g, a, src, pl, st);
+    if (d) return march_launch<T, L, F, false, true>(g, a, src, pl, st);
+    return march_launch<T, L, F, false, false>(g, a, src, pl, st);
+}
+
+template <bool T, bool L>
+int march_dispatch1(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+{
+    return a.ffs != 0.0 ? march_dispatch2<T, L, true>(g, a, src, pl, st) : march_dispatch2<T, L, false>(g, a, src, pl, st);
+}
+
+// one thread per table row
+__global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, double *__restrict__ fc)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= h) return;
+    double row[swf::FC_STRIDE];
+    swf::build_fast_row(tab, h, r, tau, row);
+#pragma unroll
+    for (int k = 0; k < swf::FC_STRIDE; ++k) fc[(long)r * swf::FC_STRIDE + k] = row[k];
+}
+
+// band_land[w] = 1 <=> no sea cell among the output cells of warp w's band
+__global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, MarchPlan pl, unsigned char *__restrict__ out)
+{
+    const int w = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (w >= pl.nwarps) return;
+    const int band = w / pl.ncol, col = w - band * pl.ncol;
+    const int nrows = pl.n1 - pl.n0 + 1;
+    const int bs = pl.n0 + (int)((long)band * nrows / pl.nbands);
+    const int be = pl.n0 + (int)((long)(band + 1) * nrows / pl.nbands) - 1;
+    const int m = g.nx_start + WOUT * col + lane;
+    int any = 0;
+    if (lane < WOUT && m <= g.nx_end)
+        for (int n = bs; n <= be; ++n) any |= mask[ix(g, m, n)] & MB_LU;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) out[w] = any ? 0 : 1;
+}
+
+}  // namespace
+
+bool march_supported(const Geo &g, const FusedArgs &a)
+{
+    // 16-byte cp.async chunks: the first staged column of every warp must be even in array coordinates
+    return a.tab != nullptr && a.fc != nullptr && (g.nx_start - 2 - g.bx1) >= 0 && (g.nx_start - 2 - g.bx1) % 2 == 0 &&
+           g.pitch % 2 == 0 && g.ny_start - 2 >= g.by1 && g.ny_end + 2 <= g.by2;
+}
+
+// Warp columns x bands for rows [n0..n1]: as many bands as keep every warp resident at once
+// (max_warps = SMs x resident warps), but bands of at least min_rows rows (each band pays 2 warm-up rows).
+void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl)
+{
+    pl->n0 = n0; pl->n1 = n1;
+    pl->ncol = (g.nx_end - g.nx_start + WOUT) / WOUT;
+    const int nrows = n1 - n0 + 1;
+    const int min_rows = 16;
+    int nb = max_warps / (pl->ncol > 0 ? pl->ncol : 1);
+    if (nb < 1) nb = 1;
+    if (nb > (nrows + min_rows - 1) / min_rows) nb = (nrows + min_rows - 1) / min_rows;
+    if (nb < 1) nb = 1;
+    pl->nbands = nb;
+    pl->nwarps = pl->ncol * nb;
+    pl->band_land = nullptr;
+}
+
+int march_resident_warps(int device)
+{
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148 * 12;
+    if (cudaFuncSetAttribute(k_march<true, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)MARCH_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false>, MW * 32,
+                                                      MARCH_SMEM) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 3;
+    }
+    return sms * per_sm * MW;
+}
+
+int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st)
+{
+    if (pl.n1 < pl.n0 || pl.nwarps < 1) return SWCU_OK;
+    MarchIn src;
+    src.in[A_SSH] = a.ssh; src.in[A_SSHP] = a.sshp; src.in[A_U] = a.u; src.in[A_UP] = a.up; src.in[A_V] = a.v;
+    src.in[A_VP] = a.vp; src.in[A_H] = a.h_r; src.in[A_MU] = a.mu;
+    if (a.trans && a.lat) return march_dispatch1<true, true>(g, a, src, pl, st);
+    if (a.trans) return march_dispatch1<true, false>(g, a, src, pl, st);
+    if (a.lat) return march_dispatch1<false, true>(g, a, src, pl, st);
+    return march_dispatch1<false, false>(g, a, src, pl, st);
+}
+
+int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st)
+{
+    k_build_fast<<<(unsigned)((h + 63) / 64), 64, 0, st>>>(tab, h, tau, fc);
+    return launched("build_fast");
+}
+
+int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st)
+{
+    if (pl.nwarps < 1) return SWCU_OK;
+    k_band_land<<<(unsigned)((pl.nwarps + 7) / 8), 256, 0, st>>>(g, mask, pl, out);
+    return launched("band_land");
+}
+
+}  // namespace swcu

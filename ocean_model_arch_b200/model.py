@@ -231,7 +231,10 @@ class BlockInputs:
 class DeviceBlock:
     """One block resident on one GPU (Level B of include/swcuda.h)."""
 
-    def __init__(self, dims: SwcuDims, sw: SwPar, device=0, mode=MODE_FUSED):
+    def __init__(self, dims: SwcuDims, sw: SwPar, device=0, mode=MODE_FUSED, exact=None):
+        """exact: True = arithmetic bitwise equal to the reference's CPU path (k_step), False = the same scheme
+        re-associated for speed (k_march; rel. L2 <= 1e-12 after 1000 steps), None = the library's default
+        (tolerance mode unless the environment says SWCU_EXACT=1)."""
         self.L = _lib.lib()
         self.dims = dims
         self.sw = sw
@@ -241,6 +244,8 @@ class DeviceBlock:
         h = C.c_void_p()
         check(self.L.swcu_create(C.byref(h), C.byref(dims), C.byref(self.params), device))
         self.h = h
+        if exact is not None and mode == MODE_FUSED:
+            self.set_option("exact", 1 if exact else 0)
 
     def upload(self, name, arr):
         want = np.float64 if name in F8_NAMES else np.float32
@@ -445,7 +450,7 @@ class ShallowWaterModel:
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, mask=None,
                  device=0, mode=MODE_FUSED, rank=0, world=1, hhq_rest=100.0, keep_mu=False, r_diss=0.0,
-                 stripe_rows=None, device_init=False, balance=False):
+                 stripe_rows=None, device_init=False, balance=False, exact=None):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
@@ -456,7 +461,7 @@ class ShallowWaterModel:
             self.dims = balanced_slab_dims(self.basin.nx, self.basin.ny, world, rank, mask)
         else:
             self.dims = block_dims(self.basin.nx, self.basin.ny, 1, world, 0, rank)
-        self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode)
+        self.block = DeviceBlock(self.dims, self.sw, device=device, mode=mode, exact=exact)
         if device_init:
             self.inputs = None
             self.block.init_on_device(self.basin, self.sw, mask, hhq_rest=hhq_rest, keep_mu=keep_mu, r_diss=r_diss,
@@ -558,7 +563,7 @@ class BlockGridModel:
 
     def __init__(self, basin: BasinPar = None, sw: SwPar = None, run: RunPar = None, *, bnx=1, bny=1, mask=None,
                  devices=(0,), mode=MODE_FUSED, hhq_rest=100.0, keep_mu=False, r_diss=0.0, skip_land_blocks=True,
-                 device_init=False, decomposition="round_robin"):
+                 device_init=False, decomposition="round_robin", exact=None):
         self.basin = basin or BasinPar()
         self.sw = sw or SwPar()
         self.run = run or RunPar()
@@ -587,7 +592,7 @@ class BlockGridModel:
                     self.land_blocks.append((bm, bn))
                     continue
                 dev = devices[len(self.grid) % len(devices)] if self.owner is None else devices[max(self.owner[bn, bm], 0)]
-                blk = DeviceBlock(d, self.sw, device=dev, mode=mode)
+                blk = DeviceBlock(d, self.sw, device=dev, mode=mode, exact=exact)
                 if device_init:
                     blk.init_on_device(self.basin, self.sw, mask, hhq_rest=hhq_rest, keep_mu=keep_mu, r_diss=r_diss)
                 else:

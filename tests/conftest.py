@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The pre-existing suites assert BITWISE equality with the oracle: they run the library in its bitwise
+# arithmetic ("exact" = 1).  The tolerance mode (the library default, k_march) has its own suites
+# (test_fast_formulas.py, test_gpu_fast.py, the multi-GPU cases of run_multi_gpu.py) that pass exact=False.
+os.environ.setdefault("SWCU_EXACT", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

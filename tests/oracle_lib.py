@@ -142,3 +142,15 @@ def call_kernel(name, dims, *args, fast=False):
             raise TypeError(type(a))
     fn.restype = C.c_int
     return fn(*cargs)
+
+
+def redo_hh_init(o):
+    """The init-time envoke(hh_init) (control/init_data.f90:60-63) again, after a test overwrote hhq_rest or
+    ssh of a one-block oracle model: refreshes the twelve depth arrays."""
+    f4 = {n: o.get(n) for n in ("lu", "llu", "llv", "luh", "dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb")}
+    outs = {n: o.get(n) for n in ("hhq", "hhq_p", "hhq_n", "hhu", "hhu_p", "hhu_n", "hhv", "hhv_p", "hhv_n",
+                                  "hhh", "hhh_p", "hhh_n")}
+    call_kernel("hh_init_kernel", o.block_dims(0), int(o.cfg.full_free_surface), *[f4[n] for n in f4],
+                *[outs[n] for n in outs], o.get("ssh"), o.get("sshp"), o.get("hhq_rest"))
+    for n, arr in outs.items():
+        o.set(n, arr)
