@@ -136,10 +136,11 @@ def lib():
     """Loads libswcuda.so; raises if it has not been built (python -m ocean_model_arch_b200.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SWCU_LIB", LIB_PATH)   # tuning builds (ocean_model_arch_b200.build.build(lib=...))
+        if not os.path.exists(path):
             raise ImportError(f"{LIB_PATH} is missing: run `python -m ocean_model_arch_b200.build` "
                               "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes

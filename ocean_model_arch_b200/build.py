@@ -40,17 +40,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), lib=None, objdir=None):
+    """extra_flags / lib / objdir: tuning variants (e.g. -DSWCU_MW=3) built beside the product library."""
+    lib = lib or LIB
+    if lib == LIB and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     objs = []
     logs = []
     for s in SOURCES:
         o = os.path.join(objdir, s.rsplit(".", 1)[0] + ".o")
-        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(r.stderr)
         if r.returncode != 0:
@@ -58,7 +60,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + s)
         objs.append(o)
     cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", LIB, *objs, "-ldl"]
+           "-o", lib, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -67,7 +69,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -197,7 +197,8 @@ struct swcu_ctx {
     double fc_tau = 0.0;
     bool fc_valid = false;
     int march_warps = 0;                      // SMs x resident warps of k_march on this device
-    MarchPlan plan_main = {0, -1, 0, 0, 0, nullptr};
+    int march_minb = 2;
+    MarchPlan plan_main = {0, -1, 0, 0, 0, nullptr, 2};
     unsigned char *band_land = nullptr;
     size_t band_land_cap = 0;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
@@ -585,7 +586,7 @@ int fused_main(swcu_ctx *c, double tau)
 
     const int ns = g.ny_start, ne = g.ny_end;
     const bool march = a.fc != nullptr && march_supported(g, a);
-    if (march && !c->march_warps) c->march_warps = march_resident_warps(c->device);
+    if (march && !c->march_warps) c->march_warps = march_resident_warps(c->device, c->march_minb);
     const bool tiled = !march && c->use_tables && c->want_tiled && step_tiled_supported(g, a);
     // rows of the main launch: everything, or the interior between the two boundary strips
     // neighbours in other processes: over NCCL (communicator) or over peer memory (swcu_peer_attach)
@@ -644,6 +645,7 @@ int fused_main(swcu_ctx *c, double tau)
             } else {
                 march_plan(g, r0, r1, c->march_warps, &pl);  // boundary strip: a few rows, no flags
             }
+            pl.minb = c->march_minb;
             RC(launch_march(g, a, pl, st));
         } else {
             RC(tiled ? launch_step_tiled(maps, g, a, r0, r1, c->tile_variant, st) : launch_update(g, a, r0, r1, st));
@@ -1154,6 +1156,11 @@ int swcu_set_option(swcu_ctx *c, const char *name, int value)
         return SWCU_OK;
     }
     if (!strcmp(name, "land_skip")) { c->want_land_skip = value != 0; return SWCU_OK; }
+    if (!strcmp(name, "march_minb")) {
+        if (value != 2 && value != 3) { set_error("march_minb must be 2 or 3"); return SWCU_ERR_ARG; }
+        c->march_minb = value; c->march_warps = 0; c->plan_main.n1 = c->plan_main.n0 - 1; c->masks_dirty = true;
+        return SWCU_OK;
+    }
     if (!strcmp(name, "exact")) { c->exact = value != 0; c->plan_main.n1 = c->plan_main.n0 - 1; c->masks_dirty = true; return SWCU_OK; }
     set_error("unknown option %s", name);
     return SWCU_ERR_ARG;

@@ -46,10 +46,11 @@ struct MarchPlan {
     int n0, n1;
     int ncol, nbands, nwarps;
     const unsigned char *band_land;  // [nwarps]: 1 <=> the warp's output cells are all land (skipped), or nullptr
+    int minb;                        // register budget variant: sized for 2 or 3 CTAs per SM
 };
 bool march_supported(const Geo &g, const FusedArgs &a);
 void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl);
-int march_resident_warps(int device);  // SMs x resident warps of k_march: the size of one full wave
+int march_resident_warps(int device, int minb);  // SMs x resident warps of k_march: the size of one full wave
 int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st);
 int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st);
 int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st);

@@ -4,15 +4,18 @@
 // Work decomposition.  A WARP owns 28 output columns (its 32 lanes carry a 2-column halo on each
 // side) and marches up a band of rows, one row per iteration.  There is no CTA-wide barrier and no
 // shared-memory tile of intermediates:
-//   - the eight input arrays (ssh, sshp, u, up, v, vp, hhq_rest, mu) arrive through a per-warp ring of
-//     RING rows in shared memory, filled with 16-byte cp.async (LDGSTS, zero-filled outside the array)
-//     RING-3 rows ahead of their use: all of a warp's HBM reads are in flight while it computes;
+//   - the eight input arrays (ssh, sshp, u, up, v, vp, hhq_rest, mu), the mask bytes and the row's
+//     coefficients arrive through a per-warp ring of RING rows in shared memory, filled with cp.async
+//     (LDGSTS, zero-filled outside the array) RING-3 rows ahead of their use: all of a warp's HBM reads
+//     are in flight while it computes, and nothing in the loop waits for a global load;
 //   - every input value is read from the ring ONCE when it enters the 3-row stencil window and then
 //     rotates through registers (row b+2 -> b+1 -> b);
 //   - stage A (depths, volume fluxes, stresses, vorticity: the quantities a U/V/H/T point owns) is
 //     evaluated one row ahead of stage B; its results rotate through registers the same way and reach
 //     the east / west neighbours by warp shuffles;
-//   - per-row coefficients come from a 256-byte table row (uniform 16-byte loads through L1).
+//   - the row's coefficients (a 256-byte table row, sw_fast.cuh) travel through the same ring and are read
+//     with broadcast 16-byte loads (as plain global loads their L2 latency was 59 % of all stall samples:
+//     profiles/r02_march_v1.txt).
 // Per cell this costs ~140 fp64 instructions, ~13 shared-memory loads and ~23 shuffles, against ~490
 // fp64 instructions and ~160 shared-memory accesses of the bitwise kernel k_step.
 //
@@ -26,14 +29,21 @@ namespace swcu {
 
 namespace {
 
-constexpr int MW = 4;      // warps per CTA (the CTA is only a container: warps never synchronise with each other)
+#ifndef SWCU_MW
+#define SWCU_MW 4
+#endif
+#ifndef SWCU_RING
+#define SWCU_RING 8
+#endif
+constexpr int MW = SWCU_MW;  // warps per CTA (the CTA is only a container: warps never synchronise with each other)
 constexpr int WOUT = 28;   // output columns per warp
 constexpr int NARR = 8;    // staged input arrays
-constexpr int RING = 8;    // rows in the per-warp ring
-constexpr int MARCH_MINB = 2;  // CTAs per SM the register budget is sized for
+constexpr int NROW = NARR + 1;  // 256-byte rows per ring slot: the eight arrays + the row's coefficients
+constexpr int RING = SWCU_RING;  // rows in the per-warp ring
 constexpr int PADW = 2;    // doubles of padding at both ends of a warp's ring (lane -1 / lane 32 reads)
-constexpr int RING_DOUBLES = RING * NARR * 32 + 2 * PADW;
-constexpr size_t MARCH_SMEM = (size_t)MW * RING_DOUBLES * sizeof(double);
+constexpr int RING_DOUBLES = RING * NROW * 32 + 2 * PADW;
+constexpr int MASK_RING_BYTES = RING * 32;  // one mask byte per lane and ring row
+constexpr size_t MARCH_SMEM = (size_t)MW * (RING_DOUBLES * sizeof(double) + MASK_RING_BYTES);
 
 enum { A_SSH, A_SSHP, A_U, A_UP, A_V, A_VP, A_H, A_MU };
 
@@ -44,37 +54,44 @@ __device__ __forceinline__ void cp16(unsigned dst, const void *src, bool valid)
     const unsigned sz = valid ? 16u : 0u;  // src-size 0: nothing is read, the 16 bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp4(unsigned dst, const void *src, bool valid)
+{
+    const unsigned sz = valid ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 64-bit shuffles as two 32-bit ones on the unpacked halves
+// 64-bit shuffles as two 32-bit ones on the unpacked halves (plain intrinsics: the compiler may schedule
+// them freely between the two unrolled rows)
 __device__ __forceinline__ double shfl_dn(double x)
 {
-    double y;
-    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; shfl.sync.down.b32 lo, lo, 1, 0x1f, 0xffffffff; "
-                 "shfl.sync.down.b32 hi, hi, 1, 0x1f, 0xffffffff; mov.b64 %0, {lo, hi}; }" : "=d"(y) : "d"(x));
-    return y;
+    const int lo = __shfl_down_sync(0xffffffffu, __double2loint(x), 1);
+    const int hi = __shfl_down_sync(0xffffffffu, __double2hiint(x), 1);
+    return __hiloint2double(hi, lo);
 }
 __device__ __forceinline__ double shfl_up(double x)
 {
-    double y;
-    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; shfl.sync.up.b32 lo, lo, 1, 0x0, 0xffffffff; "
-                 "shfl.sync.up.b32 hi, hi, 1, 0x0, 0xffffffff; mov.b64 %0, {lo, hi}; }" : "=d"(y) : "d"(x));
-    return y;
+    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(x), 1);
+    const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(x), 1);
+    return __hiloint2double(hi, lo);
 }
 
-// predicated (never branching) store
+// predicated (never branching) store.  No "memory" clobber: the output planes are never read by this
+// kernel, so the store may move freely among the shared-memory loads of the next row.
 __device__ __forceinline__ void st_if(bool pred, double *ptr, double v)
 {
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(ptr), "d"(v) : "memory");
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(ptr), "d"(v));
 }
 
 struct MarchIn {
     const double *in[NARR];  // ssh sshp u up v vp hhq_rest mu
 };
 
-template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS>
-__global__ void __launch_bounds__(MW * 32, MARCH_MINB)
+// MINB = CTAs per SM the register budget is sized for (2: 255 registers, 8 warps per SM; 3: 168 registers,
+// 12 warps per SM and a few spilled values)
+template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, int MINB>
+__global__ void __launch_bounds__(MW * 32, MINB)
 k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 {
     using namespace swf;
@@ -91,6 +108,8 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 
     double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * RING_DOUBLES + PADW;
     const unsigned ring_s = smem_addr(ring);
+    const unsigned char *mring = smem_raw + (size_t)MW * RING_DOUBLES * sizeof(double) + (size_t)wib * MASK_RING_BYTES;
+    const unsigned mring_s = smem_addr(mring);
     const int p = g.pitch, h = g.by2 - g.by1 + 1;
     const int ax = g.nx_start - 2 - g.bx1 + WOUT * col;  // array column of lane 0
     const int ac = ax + lane;                            // my array column
@@ -107,14 +126,20 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 #pragma unroll
         for (int i = 0; i < NARR / 2; ++i) {
             const double *base = half ? src.in[2 * i + 1] : src.in[2 * i];
-            cp16(ring_s + (unsigned)(((slot * NARR + 2 * i + half) * 32 + 2 * chunk) * sizeof(double)), base + off, ok);
+            cp16(ring_s + (unsigned)(((slot * NROW + 2 * i + half) * 32 + 2 * chunk) * sizeof(double)), base + off, ok);
+        }
+        // the row's coefficients (sw_fast.cuh: 32 doubles per row) ride in the same group
+        const bool rok = r >= 0 && r <= r_last && r < h;
+        if (half == 0) {
+            cp16(ring_s + (unsigned)(((slot * NROW + NARR) * 32 + 2 * chunk) * sizeof(double)),
+                 a.fc + (rok ? (long)r * swf::FC_STRIDE + 2 * chunk : 0), rok);
+        } else if (chunk < 8) {  // ... and its 32 mask bytes (4-byte chunks; 0 outside the plane)
+            const bool mok = rok && ax + 4 * chunk + 3 < p;
+            cp4(mring_s + (unsigned)(slot * 32 + 4 * chunk), a.mask + (mok ? (long)r * p + ax + 4 * chunk : 0), mok);
         }
         cp_commit();
     };
-    auto mask_at = [&](int r) -> unsigned {  // mask byte of (r, ac), 0 outside the plane
-        return (r >= 0 && r < h && ac < p) ? (unsigned)__ldg(a.mask + (long)r * p + ac) : 0u;
-    };
-#define RNG(slot, arr, dl) ring[((slot) * NARR + (arr)) * 32 + lane + (dl)]
+#define RNG(slot, arr, dl) ring[((slot) * NROW + (arr)) * 32 + lane + (dl)]
 
 #pragma unroll
     for (int j = 0; j < RING; ++j) issue_row(r_first + j, j);
@@ -133,14 +158,13 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
     S[1].A = S[0].A;
     S[0].qpm = S[0].sp = S[0].fyp = S[0].fypy = 0.0;
     S[1].qpm = S[1].sp = S[1].fyp = S[1].fypy = 0.0;
-    unsigned mb0 = 0u, mb1, lue0 = 0u, lue1, mbn;
+    unsigned mb0 = 0u, mb1, lue0 = 0u, lue1;
     float rd_n = 0.0f;
 
     // prologue: what stage A of row bs-1 needs from row bs-1 (slot 1)
-    mb1 = mask_at(r_first + 1);
-    mbn = mask_at(r_first + 2);
     cp_wait<RING - 2>();
     __syncwarp();
+    mb1 = mring[1 * 32 + lane];
     {
         const double h1 = RNG(1, A_H, 0);
         S[0].q = FFS ? h1 + RNG(1, A_SSH, 0) : h1;
@@ -153,51 +177,51 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
     const double ts_half = 0.5 * a.ts;
     const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
     int s0 = 0, s1i = 1, s2i = 2;  // ring slots of rows b, b+1, b+2
-    const double2 *fc2 = reinterpret_cast<const double2 *>(a.fc);  // a table row = 16 pairs
 
     auto row = [&](const int b, Bank &X, Bank &Y) {
         const int rb = b - g.by1;  // array row of b
-        // coefficient rows (uniform addresses, 16-byte loads; pair k = columns 2k, 2k+1 of FastCoef)
+        const double *r0 = ring + s0 * (NROW * 32) + lane, *r1 = ring + s1i * (NROW * 32) + lane,
+                     *r2 = ring + s2i * (NROW * 32) + lane;
+#define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
+
+        cp_wait<RING - 3>();  // row b+2 has landed (my copies) ...
+        __syncwarp();         // ... and everybody else's
+
+        const unsigned mb2 = mring[s2i * 32 + lane];
+        // coefficient rows from the ring (uniform addresses: broadcast 16-byte loads; pair k = columns 2k, 2k+1)
         ACoef ka;
         BCoef kb;
         {
-            const double2 *ra = fc2 + (long)(rb + 1) * (FC_STRIDE / 2), *rw = fc2 + (long)rb * (FC_STRIDE / 2);
+            const double2 *ra = reinterpret_cast<const double2 *>(ring + (s1i * NROW + NARR) * 32);
+            const double2 *rw = reinterpret_cast<const double2 *>(ring + (s0 * NROW + NARR) * 32);
             double2 t;
-            t = __ldg(ra + 0); ka.ku = t.x; ka.area = t.y;
-            t = __ldg(ra + 1); ka.area_n = t.x; ka.kv = t.y;
-            t = __ldg(ra + 2); ka.kh = t.x; ka.dyh = t.y;
-            t = __ldg(ra + 3); ka.dxh = t.x; ka.c1 = t.y;
-            t = __ldg(ra + 4); ka.c2 = t.x; ka.c3 = t.y;
-            t = __ldg(ra + 5); ka.cor = t.x; ka.s1 = t.y;
-            t = __ldg(ra + 6); ka.rxy = t.x; ka.rdxh = t.y;
-            t = __ldg(ra + 7); ka.rdxh_s = t.x; ka.rxyb = t.y;
-            t = __ldg(ra + 8); ka.rdxt = t.x; ka.rdxt_n = t.y;
-            t = __ldg(ra + 9); ka.s2 = t.x;
-            t = __ldg(rw + 0); kb.ku = t.x; kb.area = t.y;
-            t = __ldg(rw + 1); kb.area_n = t.x; kb.kv = t.y;
-            t = __ldg(rw + 9); kb.cssh = t.y;
-            t = __ldg(rw + 10); kb.cu = t.x; kb.gx = t.y;
-            t = __ldg(rw + 11); kb.dcx = t.x; kb.dxb2 = t.y;
-            t = __ldg(rw + 12); kb.dxb2_s = t.x; kb.cv = t.y;
-            t = __ldg(rw + 13); kb.gy = t.x; kb.dx2 = t.y;
-            t = __ldg(rw + 14); kb.dx2_n = t.x; kb.dcy = t.y;
-            t = __ldg(rw + 15); kb.rdxt = t.x; kb.rdxh = t.y;
+            t = ra[0]; ka.ku = t.x; ka.area = t.y;
+            t = ra[1]; ka.area_n = t.x; ka.kv = t.y;
+            t = ra[2]; ka.kh = t.x; ka.dyh = t.y;
+            t = ra[3]; ka.dxh = t.x; ka.c1 = t.y;
+            t = ra[4]; ka.c2 = t.x; ka.c3 = t.y;
+            t = ra[5]; ka.cor = t.x; ka.s1 = t.y;
+            t = ra[6]; ka.rxy = t.x; ka.rdxh = t.y;
+            t = ra[7]; ka.rdxh_s = t.x; ka.rxyb = t.y;
+            t = ra[8]; ka.rdxt = t.x; ka.rdxt_n = t.y;
+            t = ra[9]; ka.s2 = t.x;
+            t = rw[0]; kb.ku = t.x; kb.area = t.y;
+            t = rw[1]; kb.area_n = t.x; kb.kv = t.y;
+            t = rw[9]; kb.cssh = t.y;
+            t = rw[10]; kb.cu = t.x; kb.gx = t.y;
+            t = rw[11]; kb.dcx = t.x; kb.dxb2 = t.y;
+            t = rw[12]; kb.dxb2_s = t.x; kb.cv = t.y;
+            t = rw[13]; kb.gy = t.x; kb.dx2 = t.y;
+            t = rw[14]; kb.dx2_n = t.x; kb.dcy = t.y;
+            t = rw[15]; kb.rdxt = t.x; kb.rdxh = t.y;
             kb.tau = a.tau.tau;
         }
-        const unsigned mb2 = mbn;
-        mbn = mask_at(rb + 3);
-        const double *r0 = ring + s0 * (NARR * 32) + lane, *r1 = ring + s1i * (NARR * 32) + lane,
-                     *r2 = ring + s2i * (NARR * 32) + lane;
-#define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
 
         // what stage B needs from the row below (bank Y still holds row b-1), before stage A overwrites it
         const double dvh = X.A.vh - Y.A.vh;
         const double dss = south_ss(kb, X.A.ss, Y.A.ss);
         const double zxs = X.A.zx + Y.A.zx;
         const double fyp_s = X.fyp, fypy_s = X.fypy;
-
-        cp_wait<RING - 3>();  // row b+2 has landed (my copies) ...
-        __syncwarp();         // ... and everybody else's
 
         // ---- stage A, row b+1 (into bank Y)
         const double h2 = AT(r2, A_H, 0);
@@ -282,20 +306,26 @@ inline int launched(const char *what)
     return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
 }
 
-template <bool T, bool L, bool F, bool R, bool D>
-int march_launch(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+template <bool T, bool L, bool F, bool R, bool D, int MINB>
+int march_launch_b(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
 {
     static unsigned long long attr_set = 0;  // per device opt-in for > 48 KB of dynamic shared memory
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(k_march<T, L, F, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_march<T, L, F, R, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)MARCH_SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_march)");
         __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
     }
     const unsigned grid = (unsigned)((pl.nwarps + MW - 1) / MW);
-    k_march<T, L, F, R, D><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    k_march<T, L, F, R, D, MINB><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
     return launched("k_march");
+}
+template <bool T, bool L, bool F, bool R, bool D>
+int march_launch(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+{
+    return pl.minb == 3 ? march_launch_b<T, L, F, R, D, 3>(g, a, src, pl, st) : march_launch_b<T, L, F, R, D, 2>(g, a, src, pl, st);
 }
 
 template <bool T, bool L, bool F>
@@ -347,8 +377,10 @@ __global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, March
 bool march_supported(const Geo &g, const FusedArgs &a)
 {
     // 16-byte cp.async chunks: the first staged column of every warp must be even in array coordinates
-    return a.tab != nullptr && a.fc != nullptr && (g.nx_start - 2 - g.bx1) >= 0 && (g.nx_start - 2 - g.bx1) % 2 == 0 &&
-           g.pitch % 2 == 0 && g.ny_start - 2 >= g.by1 && g.ny_end + 2 <= g.by2;
+    // 16-byte chunks of the arrays and 4-byte chunks of the mask plane: the first staged column of a warp
+    // (28 columns apart) must be a multiple of 4 in array coordinates
+    return a.tab != nullptr && a.fc != nullptr && (g.nx_start - 2 - g.bx1) >= 0 && (g.nx_start - 2 - g.bx1) % 4 == 0 &&
+           g.pitch % 4 == 0 && g.ny_start - 2 >= g.by1 && g.ny_end + 2 <= g.by2;
 }
 
 // Warp columns x bands for rows [n0..n1]: as many bands as keep every warp resident at once
@@ -366,19 +398,24 @@ void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl)
     pl->nbands = nb;
     pl->nwarps = pl->ncol * nb;
     pl->band_land = nullptr;
+    pl->minb = 2;
 }
 
-int march_resident_warps(int device)
+int march_resident_warps(int device, int minb)
 {
     int sms = 0, per_sm = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148 * 12;
-    if (cudaFuncSetAttribute(k_march<true, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)MARCH_SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false>, MW * 32,
-                                                      MARCH_SMEM) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        per_sm = 3;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148 * 4 * minb;
+    cudaError_t e;
+    if (minb == 3) {
+        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 3>, MW * 32, MARCH_SMEM);
+    } else {
+        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 2>, MW * 32, MARCH_SMEM);
     }
+    if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = minb; }
     return sms * per_sm * MW;
 }
 
