@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag = True
@@ -105,7 +105,7 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def cpu_port_rate(size, steps, warmup, budget_s=25.0):
+def cpu_port_rate(size, steps, warmup, budget_s=25.0, gpus=1, curve_grid=1):
     """Times the CPU oracle (-O3 -march=native -fopenmp build made on THIS box) on the same basin:
     one block per thread (y-slabs), omp-for over blocks per kernel + halo copies, like the
     reference's _MPP_BLOCK_MODE_ (core/kernel_interface.f90:84-101).  Returns (cells/s, info)."""
@@ -115,9 +115,9 @@ def cpu_port_rate(size, steps, warmup, budget_s=25.0):
                           stdout=subprocess.DEVNULL)
     from oracle_lib import OracleModel, make_config
     nthreads = cpu_threads()
-    bny = max(1, min(nthreads, size // 8))
-    n = size + 4
-    m = OracleModel(make_config(n, n, bnx=1, bny=bny, nthreads=nthreads), None, fast=True)
+    bny = max(1, min(nthreads, size * gpus // 8))
+    nx, ny = size + 4, size * gpus + 4     # the basin the GPU arm runs on `gpus` GPUs (weak scaling)
+    m = OracleModel(make_config(nx, ny, bnx=1, bny=bny, nthreads=nthreads, curve_grid=curve_grid), None, fast=True)
     t0 = time.perf_counter()
     m.step(max(1, warmup))
     per = (time.perf_counter() - t0) / max(1, warmup)
@@ -126,9 +126,9 @@ def cpu_port_rate(size, steps, warmup, budget_s=25.0):
     t0 = time.perf_counter()
     m.step(steps)
     dt = time.perf_counter() - t0
-    cells = size * size
+    cells = size * size * gpus
     info = {"cores": nthreads, "blocks": f"1x{bny}", "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "sample": f"{steps} steps of the {size}x{size} basin, {bny} y-slab blocks on {nthreads} threads"}
+            "sample": f"{steps} steps of the {size}x{size * gpus} basin, {bny} y-slab blocks on {nthreads} threads"}
     m.close()
     return cells * steps / dt, info
 
@@ -136,12 +136,13 @@ def cpu_port_rate(size, steps, warmup, budget_s=25.0):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    rate, info = cpu_port_rate(args.size, args.steps, args.warmup)
+    args.curve_grid = 0 if (args.cartesian or args.size * args.gpus + 4 > 8200) else 1
+    rate, info = cpu_port_rate(args.size, args.steps, args.warmup, gpus=args.gpus, curve_grid=args.curve_grid)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": info["steps"], "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,6 +174,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reps", type=int, default=5, help="repetitions of the K-step timed region (median is reported)")
     ap.add_argument("--size", type=int, default=2048, help="computational cells per GPU along each axis")
     ap.add_argument("--mode", default="fused", choices=["fused", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,21 +297,38 @@ def main():
 
     total_cells = sum_over_ranks(float(cells))   # slabs may differ in height (--balance, ragged splits)
 
-    # ---- resident run: the headline `value`
-    sampler = ClockSampler(local_rank)   # nvmlInit is slow and serialises across processes: before the barrier
+    # ---- resident run: the headline `value`.  `reps` repetitions of EXACTLY K steps, each bracketed by
+    # barrier + synchronize on both sides and timed with CUDA events on the context's stream; a repetition
+    # counts with the MAX over ranks, the reported one is the median repetition (a 20-step region lasts a
+    # few milliseconds: a single one would measure the ranks' start skew, not the step).
+    sampler = ClockSampler(local_rank)   # nvmlInit is slow and serialises across processes: before any barrier
     m.step(args.warmup)
     assert blk.synchronize() == 0
     barrier()
     sampler.start()
-    l0 = blk.launches
-    blk.timer_start()
-    m.step(args.steps)
-    ms = blk.timer_stop()
-    launches = blk.launches - l0
-    assert blk.synchronize() == 0
+    rep_ms, launches = [], 0
+    for _ in range(max(1, args.reps)):
+        barrier()
+        l0 = blk.launches
+        blk.timer_start()
+        m.step(args.steps)
+        rep_ms.append(blk.timer_stop())
+        launches = blk.launches - l0
+        assert blk.synchronize() == 0
     barrier()
     clocks = sampler.result()
-    ms = max_over_ranks(ms)
+    if world > 1:
+        allms = [None] * world
+        dist.all_gather_object(allms, rep_ms)
+    else:
+        allms = [rep_ms]
+    rep_max = [max(r[i] for r in allms) for i in range(len(rep_ms))]
+    order = sorted(range(len(rep_max)), key=lambda i: rep_max[i])
+    mid = order[len(order) // 2]
+    ms = rep_max[mid]
+    timing = {"reps": len(rep_ms), "ms_per_rep_max_over_ranks": rep_max, "reported": "median repetition",
+              "per_rank_ms_of_reported_rep": [r[mid] for r in allms],
+              "rank_spread_ms": max(r[mid] for r in allms) - min(r[mid] for r in allms)}
     value = total_cells * args.steps / (ms * 1e-3)
 
     # ---- second pass of the same K steps with CUDA events around every launch -> per-kernel time
@@ -331,11 +350,14 @@ def main():
             ach = bpc * upd_cells / (upd_ms * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
-            kname = "k_step" if tiled else "k_update"
+            exact_mode = bool(args.exact) if args.exact is not None else os.environ.get("SWCU_EXACT", "0") not in ("", "0")
+            kname = ("k_step" if exact_mode else "k_march") if tiled else "k_update"
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get(kname, {}).get(str(S))
             roof = {"bound": "hbm",
-                    "kernel": "k_step (K1..K11 in one TMA-tiled launch)" if tiled else "k_update (K1+K4+K6+K7+K8+K11 fused)",
+                    "kernel": ("k_step (K1..K11 in one TMA-tiled launch, bitwise arithmetic)" if exact_mode else
+                               "k_march (K1..K11 in one launch: warp-marching rows, cp.async ring, tolerance arithmetic)")
+                    if tiled else "k_update (K1+K4+K6+K7+K8+K11 fused)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "bytes_per_cell": bpc, "cells_per_launch": upd_cells,
                     "ms_per_launch": upd_ms, "launches_per_step": n_upd.value / steps_prof,
@@ -343,7 +365,7 @@ def main():
                     "step_frac_vs_reference_granularity_1196B": B_REF_STEP * (value / world) / 1e9 / peak,
                     "step_frac_vs_floor_196B": B_MIN_STEP * (value / world) / 1e9 / peak}
             if tiled and os.path.exists(tp):
-                pipes = json.load(open(tp)).get("k_step_pipes", {}).get(str(S))
+                pipes = json.load(open(tp)).get(kname + "_pipes", {}).get(str(S))
                 if pipes:   # what actually bounds the fused kernel (from the committed ncu capture, not measured live)
                     roof["limiting_units_ncu"] = pipes
             if mask is not None and tiled:
@@ -464,7 +486,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "timing": timing, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "device_bytes": blk.device_bytes,
                 "halo": None if world == 1 else (
                     "boundary rows stored into the neighbours' memory over NVLink (CUDA IPC), streams wait on step "

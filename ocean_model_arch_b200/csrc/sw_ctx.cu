@@ -121,6 +121,23 @@ int wait_value_load()
     return SWCU_OK;
 }
 
+// cuStreamWriteValue64: a stream-ordered 8-byte store (here: into a neighbour's peer-mapped flag word)
+WaitValueFn g_write_value = nullptr;
+int write_value_load()
+{
+    if (g_write_value) return SWCU_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuStreamWriteValue64 not available from the driver");
+        cudaGetLastError();
+        return SWCU_ERR_CUDA;
+    }
+    g_write_value = (WaitValueFn)fn;
+    return SWCU_OK;
+}
+
 #define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
 const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
@@ -177,7 +194,7 @@ struct swcu_ctx {
         std::vector<void *> opened;
     } peer[2];                                // 0 = below (rank-1), 1 = above (rank+1)
     unsigned long long *flags = nullptr;      // mine: READY lo/hi, FREE lo/hi, READY_FF lo/hi
-    unsigned *push_count = nullptr;           // CTA counters of k_push_halo (one per stream)
+    unsigned *push_count = nullptr;           // counters: [0,1] k_push_halo, [2,3] strip warps of k_march
     double *set_ptr[2][8] = {};               // my planes in export order
     int cur_set = 0;                          // set_ptr[cur_set] holds the current state
     // per-row metric tables (FUSED): rebuilt after a metric upload, used when all arrays are row-constant
@@ -198,7 +215,8 @@ struct swcu_ctx {
     bool fc_valid = false;
     int march_warps = 0;                      // SMs x resident warps of k_march on this device
     int march_minb = 2;
-    MarchPlan plan_main = {0, -1, 0, 0, 0, nullptr, 2};
+    MarchPlan plan_main = {0, -1, 0, 0, 0, 0, 0, 0, nullptr, 2};
+    int plan_sides = -1;
     unsigned char *band_land = nullptr;
     size_t band_land_cap = 0;
     std::map<const void *, CUtensorMap> tmaps;  // TMA descriptors by array base pointer
@@ -596,9 +614,26 @@ int fused_main(swcu_ctx *c, double tau)
     int main0 = ns, main1 = ne;
     if (lo) main0 = (ns + 1 < ne ? ns + 1 : ne) + 1;
     if (hi && main0 <= ne) main1 = (ne - 1 > main0 ? ne - 1 : main0) - 1;
-    if (march && (c->masks_dirty || c->plan_main.n0 != main0 || c->plan_main.n1 != main1)) {
+    // tolerance mode over peer memory: ONE launch per step, the boundary strips and their push into the
+    // neighbours' halo rows are part of k_march (MarchPeer)
+    const bool fused_push = march && peers && (ne - ns + 1) >= 4;
+    const int sides = fused_push ? (lo ? 1 : 0) + (hi ? 2 : 0) : 0;
+    if (march && (c->masks_dirty || c->plan_main.n0 != main0 || c->plan_main.n1 != main1 || c->plan_sides != sides)) {
         // geometry of the main launch and the all-land flags of its bands
         march_plan(g, main0, main1, c->march_warps, &c->plan_main);
+        c->plan_sides = sides;
+        if (sides) {
+            // the lowest / highest band's warps do the boundary strip first (about ten row iterations incl. the
+            // second ring start-up): those bands get that much less to do
+            int cut = 10;
+            if (const char *e = getenv("SWCU_LATE_CUT")) cut = atoi(e);
+            const int nb = c->plan_main.nbands;
+            if ((main1 - main0 + 1) / nb > 4 * cut && (nb > 1 || sides != 3)) {
+                c->plan_main.late_lo = (sides & 1) ? 1 : 0;
+                c->plan_main.late_hi = (sides & 2) ? 1 : 0;
+                c->plan_main.late_cut = cut;
+            }
+        }
         const size_t need = (size_t)(c->plan_main.nwarps > 0 ? c->plan_main.nwarps : 1);
         if (need > c->band_land_cap) {
             if (c->band_land) { cudaFree(c->band_land); c->bytes -= (long)c->band_land_cap; }
@@ -656,6 +691,40 @@ int fused_main(swcu_ctx *c, double tau)
     };
     if (!lo && !hi) {
         RC(rows(ns, ne, c->st));
+    } else if (fused_push) {
+        const unsigned long long tick = (unsigned long long)c->steps_done + 1;
+        // my write buffers may be written by the neighbours from here on (everything that read them has been
+        // issued before on this stream): two stream-ordered stores into their flag words, no kernel
+        RC(write_value_load());
+        for (int side = 0; side < 2; ++side) {
+            if (!c->peer[side].on) continue;
+            CUresult r = g_write_value((CUstream)c->st, (CUdeviceptr)(c->peer[side].flags + (side == 0 ? 3 : 2)), tick, 0);
+            if (r != CUDA_SUCCESS) { set_error("cuStreamWriteValue64 failed with %d", (int)r); return SWCU_ERR_CUDA; }
+        }
+        MarchPeer mp;
+        memset(&mp, 0, sizeof(mp));
+        const int e = ns + 1, s2 = ne - 1;
+        mp.lo0 = ns; mp.lo1 = lo ? e : ns - 1; mp.hi0 = s2; mp.hi1 = hi ? ne : s2 - 1;
+        const int wset = c->cur_set ^ 1;
+        for (int side = 0; side < 2; ++side) {
+            const swcu_ctx::PeerLink &pl = c->peer[side];
+            if (!pl.on) continue;
+            const long shift = (long)(c->d.bnd_y1 - pl.by1) * c->pitch;  // same global (m, n) in the neighbour's plane
+            for (int k = 0; k < 6; ++k) mp.out[side][k] = pl.set[wset][k] + shift;
+            mp.ready[side] = pl.flags + (side == 0 ? 1 : 0);   // I am the block above my lower neighbour
+            mp.free_[side] = c->flags + 2 + side;
+            mp.count[side] = c->push_count + 2 + side;
+        }
+        mp.tick = tick;
+        if (const char *e = getenv("SWCU_PEER_DBG")) mp.dbg = atoi(e);
+        MarchPlan pl = c->plan_main;
+        pl.band_land = c->want_land_skip ? c->band_land : nullptr;
+        pl.minb = c->march_minb;
+        RC(prof_mark(c, 1, true, c->st));
+        RC(launch_march(g, a, pl, c->st, &mp));
+        RC(prof_mark(c, 1, false, c->st));
+        c->launches++;
+        RC(peer_wait(c, c->st, 0, tick));   // my halo rows of the new state have arrived
     } else {
         // The two boundary strips (the rows each neighbour needs) run on a high-priority stream
         // concurrently with the interior update; their completion releases the exchange on a second
@@ -1064,7 +1133,7 @@ int swcu_create(swcu_ctx **out, const swcu_dims *dims, const swcu_params *params
         for (int f = 100; f < SWCU_F4_END; ++f) if (fused_keeps4(c, f)) TRY(alloc4(c, f));
         TRY(dev_alloc(c, (void **)&c->mask, c->plane));
         TRY(dev_alloc(c, (void **)&c->flags, 8 * sizeof(unsigned long long)));
-        TRY(dev_alloc(c, (void **)&c->push_count, 2 * sizeof(unsigned)));
+        TRY(dev_alloc(c, (void **)&c->push_count, 8 * sizeof(unsigned)));
         for (int i = 0; i < 6; ++i) { c->set_ptr[0][i] = c->f8[kState[i]]; c->set_ptr[1][i] = c->alt[i]; }
         if (params->use_tracers) {
             c->set_ptr[0][6] = c->f8[SWCU_F_FF1]; c->set_ptr[0][7] = c->f8[SWCU_F_FF1P];

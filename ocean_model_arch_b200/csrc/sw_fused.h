@@ -44,14 +44,45 @@ struct FusedArgs {
 // columns) and on band w / ncol of the rows [n0..n1] (bands of equal height, +-1 row).
 struct MarchPlan {
     int n0, n1;
-    int ncol, nbands, nwarps;
+    int ncol, nbands, nwarps;        // nwarps = ncol * nbands
+    // Fused halo push (MarchPeer): the warps of band 0 first work on the lower boundary strip, those of band
+    // nbands-1 on the upper one; such a band is `late_cut` rows shorter than the others (a strip costs about
+    // that many row iterations), so all warps of the launch finish together.
+    int late_lo, late_hi, late_cut;
     const unsigned char *band_land;  // [nwarps]: 1 <=> the warp's output cells are all land (skipped), or nullptr
     int minb;                        // register budget variant: sized for 2 or 3 CTAs per SM
 };
+// Halo push fused into k_march (neighbouring blocks in other processes of the node, peer-mapped memory):
+// the warps of the lowest / highest band first compute the boundary strip of their side, store it ALSO into
+// that neighbour's halo rows over NVLink, and the last of them publishes `tick` in the neighbour's "halo
+// ready" word; then they march their own band like everybody else.
+// Side 0 = the block below (rank-1), 1 = the block above.  A side is active iff out[side][0] != nullptr.
+struct MarchPeer {
+    int lo0, lo1, hi0, hi1;              // rows of the lower / upper strip (inclusive; empty if x1 < x0)
+    double *out[2][6];                   // the neighbours' write planes, shifted so that MY element index applies
+    unsigned long long *ready[2];        // the neighbours' "halo ready" words (peer-mapped)
+    const unsigned long long *free_[2];  // my "your rows in my write buffers may be overwritten" words
+    unsigned long long tick;
+    unsigned *count[2];                  // strip-warp counters (zero between launches)
+    int dbg;                             // timing experiments only (SWCU_PEER_DBG): 1 = no wait for "free", 2 = no peer stores
+};
+// rows [*bs .. *be] of band `band`
+__host__ __device__ inline int march_band_start(const MarchPlan &pl, int band)
+{
+    const long R = (long)(pl.n1 - pl.n0 + 1) + (long)pl.late_cut * (pl.late_lo + pl.late_hi);
+    return pl.n0 + (int)((long)band * R / pl.nbands) - (band >= 1 ? pl.late_lo * pl.late_cut : 0) -
+           (band == pl.nbands ? pl.late_hi * pl.late_cut : 0);
+}
+__host__ __device__ inline void march_band_rows(const MarchPlan &pl, int band, int *bs, int *be)
+{
+    *bs = march_band_start(pl, band);
+    *be = march_band_start(pl, band + 1) - 1;
+}
 bool march_supported(const Geo &g, const FusedArgs &a);
 void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl);
 int march_resident_warps(int device, int minb);  // SMs x resident warps of k_march: the size of one full wave
-int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st);
+int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer = nullptr);
+int march_strip_warps(const Geo &g);  // warps one boundary strip takes (= warp columns)
 int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st);
 int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st);
 

@@ -21,7 +21,9 @@
 //
 // Launch geometry: ncol = ceil(columns / 28) warp columns x nbands bands of rows, nbands chosen so
 // that all warps are resident at once (one wave, equal work).  Boundary strips of a multi-GPU step
-// are the same kernel on 2 rows.
+// are the same kernel on 2 rows (NCCL path) or part of the launch (peer memory: MarchPeer).
+#include <cstring>
+
 #include "sw_fast.cuh"
 #include "sw_fused.h"
 
@@ -88,24 +90,14 @@ struct MarchIn {
     const double *in[NARR];  // ssh sshp u up v vp hhq_rest mu
 };
 
-// MINB = CTAs per SM the register budget is sized for (2: 255 registers, 8 warps per SM; 3: 168 registers,
-// 12 warps per SM and a few spilled values)
-template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, int MINB>
-__global__ void __launch_bounds__(MW * 32, MINB)
-k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
+// One warp's march over rows [bs..be] of warp column `col`.  PUSH: the warp works on a boundary strip and
+// stores its results also into the neighbour's halo rows (side 0 = below, 1 = above).
+template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, bool PUSH>
+__device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPeer &peer,
+                                           unsigned char *smem_raw, const int lane, const int wib, const int col,
+                                           const int bs, const int be, const int side)
 {
     using namespace swf;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int wid = blockIdx.x * MW + wib;
-    if (wid >= pl.nwarps) return;
-    const int band = wid / pl.ncol, col = wid - band * pl.ncol;
-    const int nrows = pl.n1 - pl.n0 + 1;
-    const int bs = pl.n0 + (int)((long)band * nrows / pl.nbands);
-    const int be = pl.n0 + (int)((long)(band + 1) * nrows / pl.nbands) - 1;
-    if (be < bs) return;
-    if (pl.band_land && pl.band_land[wid]) return;  // every output cell of this warp's band is land
-
     double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * RING_DOUBLES + PADW;
     const unsigned ring_s = smem_addr(ring);
     const unsigned char *mring = smem_raw + (size_t)MW * RING_DOUBLES * sizeof(double) + (size_t)wib * MASK_RING_BYTES;
@@ -177,6 +169,14 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
     const double ts_half = 0.5 * a.ts;
     const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
     int s0 = 0, s1i = 1, s2i = 2;  // ring slots of rows b, b+1, b+2
+
+    // strip warps: the neighbour's planes (nullptr for band warps)
+    double *p_ssh = nullptr, *p_sshp = nullptr, *p_u = nullptr, *p_up = nullptr, *p_v = nullptr, *p_vp = nullptr;
+    if (PUSH) {
+        p_ssh = side ? peer.out[1][0] : peer.out[0][0]; p_sshp = side ? peer.out[1][1] : peer.out[0][1];
+        p_u = side ? peer.out[1][2] : peer.out[0][2]; p_up = side ? peer.out[1][3] : peer.out[0][3];
+        p_v = side ? peer.out[1][4] : peer.out[0][4]; p_vp = side ? peer.out[1][5] : peer.out[0][5];
+    }
 
     auto row = [&](const int b, Bank &X, Bank &Y) {
         const int rb = b - g.by1;  // array row of b
@@ -284,6 +284,22 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
         st_if(wu, a.u_o + gc, o.un); st_if(wu, a.up_o + gc, o.upf);
         st_if(wv, a.v_o + gc, o.vn); st_if(wv, a.vp_o + gc, o.vpf);
         if (sea && ssh_bad(o.sshn)) atomicAdd(a.bad, 1);  // K11
+        if (PUSH && b >= bs) {
+            // boundary strip: the same cells go straight into the neighbour's halo rows (NVLink stores).  The
+            // neighbour must have declared those rows of its write buffers free for this step.
+            if (b == bs && !(peer.dbg & 1)) {
+                if (lane == 0) {
+                    const volatile unsigned long long *f = side ? peer.free_[1] : peer.free_[0];
+                    while (*f < peer.tick) __nanosleep(64);
+                }
+                __syncwarp();
+                __threadfence_system();
+            }
+            const bool ps = !(peer.dbg & 2);
+            st_if(sea && ps, p_ssh + gc, o.sshn); st_if(sea && ps, p_sshp + gc, o.sshpf);
+            st_if(wu && ps, p_u + gc, o.un); st_if(wu && ps, p_up + gc, o.upf);
+            st_if(wv && ps, p_v + gc, o.vn); st_if(wv && ps, p_vp + gc, o.vpf);
+        }
 #undef AT
 
         // ---- row b leaves the window: refill its ring slot
@@ -300,48 +316,94 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 #undef RNG
 }
 
+// MINB = CTAs per SM the register budget is sized for (2: 255 registers, 8 warps per SM; 3: 168 registers,
+// 12 warps per SM and a few spilled values).  PEER: the launch carries boundary strips whose results are also
+// pushed into the neighbours' memory (the edge bands' warps run the PUSH body first, then everybody the lean one).
+template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, int MINB, bool PEER>
+__global__ void __launch_bounds__(MW * 32, MINB)
+k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wid = blockIdx.x * MW + wib;
+    if (wid >= pl.nwarps) return;
+    const int w = wid;
+    const int band = w / pl.ncol, col = w - band * pl.ncol;
+    if (PEER) {
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            if (peer.out[side][0] == nullptr || band != (side ? pl.nbands - 1 : 0)) continue;
+            // boundary strip of this side: compute, push, publish -- before my own band
+            const int ss = side == 0 ? peer.lo0 : peer.hi0, se = side == 0 ? peer.lo1 : peer.hi1;
+            if (se >= ss) march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, true>(g, a, src, peer, smem_raw, lane, wib, col, ss, se, side);
+            __threadfence_system();  // every lane: its stores into the neighbour's memory are visible system-wide ...
+            __syncwarp();
+            if (lane == 0) {          // ... before the last strip warp of this side publishes the step counter there
+                unsigned *cnt = side ? peer.count[1] : peer.count[0];
+                if (atomicAdd(cnt, 1u) == (unsigned)pl.ncol - 1u) {
+                    *cnt = 0;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long *>(side ? peer.ready[1] : peer.ready[0]) = peer.tick;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    int bs, be;
+    march_band_rows(pl, band, &bs, &be);
+    if (be < bs) return;
+    if (pl.band_land && pl.band_land[w]) return;  // every output cell of this warp's band is land
+    march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, false>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, -1);
+}
+
 inline int launched(const char *what)
 {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SWCU_OK : cuda_fail(e, what);
 }
 
-template <bool T, bool L, bool F, bool R, bool D, int MINB>
-int march_launch_b(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+template <bool T, bool L, bool F, bool R, bool D, int MINB, bool PEER>
+int march_launch_b(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, const MarchPeer &peer,
+                   cudaStream_t st)
 {
     static unsigned long long attr_set = 0;  // per device opt-in for > 48 KB of dynamic shared memory
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(k_march<T, L, F, R, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_march<T, L, F, R, D, MINB, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)MARCH_SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_march)");
         __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
     }
     const unsigned grid = (unsigned)((pl.nwarps + MW - 1) / MW);
-    k_march<T, L, F, R, D, MINB><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    k_march<T, L, F, R, D, MINB, PEER><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl, peer);
     return launched("k_march");
 }
 template <bool T, bool L, bool F, bool R, bool D>
-int march_launch(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+int march_launch(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, const MarchPeer &peer,
+                 cudaStream_t st)
 {
-    return pl.minb == 3 ? march_launch_b<T, L, F, R, D, 3>(g, a, src, pl, st) : march_launch_b<T, L, F, R, D, 2>(g, a, src, pl, st);
+    if (peer.out[0][0] || peer.out[1][0]) return march_launch_b<T, L, F, R, D, 2, true>(g, a, src, pl, peer, st);
+    return pl.minb == 3 ? march_launch_b<T, L, F, R, D, 3, false>(g, a, src, pl, peer, st)
+                        : march_launch_b<T, L, F, R, D, 2, false>(g, a, src, pl, peer, st);
 }
 
 template <bool T, bool L, bool F>
-int march_dispatch2(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+int march_dispatch2(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, const MarchPeer &peer,
+                    cudaStream_t st)
 {
     const bool r = a.RHSx != nullptr, d = a.rdis != nullptr;
-    if (r && d) return march_launch<T, L, F, true, true>(g, a, src, pl, st);
-    if (r) return march_launch<T, L, F, true, false>(g, a, src, pl, st);
-    if (d) return march_launch<T, L, F, false, true>(g, a, src, pl, st);
-    return march_launch<T, L, F, false, false>(g, a, src, pl, st);
+    if (r && d) return march_launch<T, L, F, true, true>(g, a, src, pl, peer, st);
+    if (r) return march_launch<T, L, F, true, false>(g, a, src, pl, peer, st);
+    if (d) return march_launch<T, L, F, false, true>(g, a, src, pl, peer, st);
+    return march_launch<T, L, F, false, false>(g, a, src, pl, peer, st);
 }
 
 template <bool T, bool L>
-int march_dispatch1(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, cudaStream_t st)
+int march_dispatch1(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPlan &pl, const MarchPeer &peer,
+                    cudaStream_t st)
 {
-    return a.ffs != 0.0 ? march_dispatch2<T, L, true>(g, a, src, pl, st) : march_dispatch2<T, L, false>(g, a, src, pl, st);
+    return a.ffs != 0.0 ? march_dispatch2<T, L, true>(g, a, src, pl, peer, st) : march_dispatch2<T, L, false>(g, a, src, pl, peer, st);
 }
 
 // one thread per table row
@@ -359,11 +421,10 @@ __global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, 
 __global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, MarchPlan pl, unsigned char *__restrict__ out)
 {
     const int w = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
-    if (w >= pl.nwarps) return;
+    if (w >= pl.ncol * pl.nbands) return;
     const int band = w / pl.ncol, col = w - band * pl.ncol;
-    const int nrows = pl.n1 - pl.n0 + 1;
-    const int bs = pl.n0 + (int)((long)band * nrows / pl.nbands);
-    const int be = pl.n0 + (int)((long)(band + 1) * nrows / pl.nbands) - 1;
+    int bs, be;
+    march_band_rows(pl, band, &bs, &be);
     const int m = g.nx_start + WOUT * col + lane;
     int any = 0;
     if (lane < WOUT && m <= g.nx_end)
@@ -399,6 +460,7 @@ void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl)
     pl->nwarps = pl->ncol * nb;
     pl->band_land = nullptr;
     pl->minb = 2;
+    pl->late_lo = pl->late_hi = pl->late_cut = 0;
 }
 
 int march_resident_warps(int device, int minb)
@@ -407,28 +469,33 @@ int march_resident_warps(int device, int minb)
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148 * 4 * minb;
     cudaError_t e;
     if (minb == 3) {
-        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 3>, MW * 32, MARCH_SMEM);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 3, false>, MW * 32, MARCH_SMEM);
     } else {
-        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        e = cudaFuncSetAttribute(k_march<true, true, true, false, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 2>, MW * 32, MARCH_SMEM);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_march<true, true, true, false, false, 2, false>, MW * 32, MARCH_SMEM);
     }
     if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = minb; }
     return sms * per_sm * MW;
 }
 
-int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st)
+int march_strip_warps(const Geo &g) { return (g.nx_end - g.nx_start + WOUT) / WOUT; }
+
+int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer_in)
 {
-    if (pl.n1 < pl.n0 || pl.nwarps < 1) return SWCU_OK;
+    if (pl.nwarps < 1 || (pl.n1 < pl.n0 && !peer_in)) return SWCU_OK;
+    MarchPeer peer;
+    if (peer_in) peer = *peer_in;
+    else memset(&peer, 0, sizeof(peer));
     MarchIn src;
     src.in[A_SSH] = a.ssh; src.in[A_SSHP] = a.sshp; src.in[A_U] = a.u; src.in[A_UP] = a.up; src.in[A_V] = a.v;
     src.in[A_VP] = a.vp; src.in[A_H] = a.h_r; src.in[A_MU] = a.mu;
-    if (a.trans && a.lat) return march_dispatch1<true, true>(g, a, src, pl, st);
-    if (a.trans) return march_dispatch1<true, false>(g, a, src, pl, st);
-    if (a.lat) return march_dispatch1<false, true>(g, a, src, pl, st);
-    return march_dispatch1<false, false>(g, a, src, pl, st);
+    if (a.trans && a.lat) return march_dispatch1<true, true>(g, a, src, pl, peer, st);
+    if (a.trans) return march_dispatch1<true, false>(g, a, src, pl, peer, st);
+    if (a.lat) return march_dispatch1<false, true>(g, a, src, pl, peer, st);
+    return march_dispatch1<false, false>(g, a, src, pl, peer, st);
 }
 
 int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st)
@@ -439,8 +506,9 @@ int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStre
 
 int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st)
 {
-    if (pl.nwarps < 1) return SWCU_OK;
-    k_band_land<<<(unsigned)((pl.nwarps + 7) / 8), 256, 0, st>>>(g, mask, pl, out);
+    const int n = pl.ncol * pl.nbands;
+    if (n < 1 || pl.n1 < pl.n0) return SWCU_OK;
+    k_band_land<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(g, mask, pl, out);
     return launched("band_land");
 }
 
