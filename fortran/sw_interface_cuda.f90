@@ -5,7 +5,7 @@
 ! tested here (the same C ABI is exercised through ctypes in tests/).  Nothing in the reference's
 ! algorithm layer (control/, core/) changes except the three call sites listed in INTEGRATION.md.
 !
-!   swcuda_c_binding                      bind(C) interfaces of the C ABI
+!   swcuda_c_binding                      bind(C) interfaces of the WHOLE C ABI (separate, generated file)
 !   shallow_water_interface_cuda_module   init_device_data_cuda, expl_shallow_water_cuda,
 !                                         download_ssh_cuda, finalize_device_data_cuda, and the
 !                                         14 envoke_<name>_kernel_cuda / _sync_cuda pairs
@@ -15,165 +15,8 @@
 ! bppnx x bppny blocks (dealt over the visible GPUs): they are linked pairwise and step together
 ! through swcu_step_group, which pulls halos device-to-device.
 !-----------------------------------------------------------------------------------------------
-module swcuda_c_binding
-    use iso_c_binding
-    implicit none
-
-    integer(c_int), parameter :: SWCU_OK = 0
-    integer(c_int), parameter :: SWCU_MODE_REFERENCE = 0, SWCU_MODE_FUSED = 1
-    integer, parameter :: SWCU_PEER_BLOB_BYTES = 2048
-
-    ! enum swcu_field (include/swcuda.h)
-    integer(c_int), parameter :: SWCU_F_SSH = 0, SWCU_F_SSHN = 1, SWCU_F_SSHP = 2,                &
-                                 SWCU_F_UBRTR = 3, SWCU_F_UBRTRN = 4, SWCU_F_UBRTRP = 5,          &
-                                 SWCU_F_VBRTR = 6, SWCU_F_VBRTRN = 7, SWCU_F_VBRTRP = 8,          &
-                                 SWCU_F_RHSX = 9, SWCU_F_RHSY = 10, SWCU_F_MU = 15,               &
-                                 SWCU_F_HHQ_REST = 19, SWCU_F_FF1 = 34, SWCU_F_FF1N = 35, SWCU_F_FF1P = 36
-    integer(c_int), parameter :: SWCU_F_LU = 100, SWCU_F_LUU = 101, SWCU_F_LUH = 102, SWCU_F_LCU = 103,  &
-                                 SWCU_F_LCV = 104, SWCU_F_LLU = 105, SWCU_F_LLV = 106,                   &
-                                 SWCU_F_DX = 107, SWCU_F_DY = 108, SWCU_F_DXT = 109, SWCU_F_DYT = 110,   &
-                                 SWCU_F_DXH = 111, SWCU_F_DYH = 112, SWCU_F_DXB = 113, SWCU_F_DYB = 114, &
-                                 SWCU_F_RLH_S = 115, SWCU_F_R_DISS = 116
-
-    ! enum swcu_kernel (include/swcuda.h)
-    integer(c_int), parameter :: SWCU_K_SW_UPDATE_SSH = 1
-    integer(c_int), parameter :: SWCU_K_HH_UPDATE = 2
-    integer(c_int), parameter :: SWCU_K_UV_TRANS_VORT = 3
-    integer(c_int), parameter :: SWCU_K_UV_TRANS = 4
-    integer(c_int), parameter :: SWCU_K_STRESS_COMPONENTS = 5
-    integer(c_int), parameter :: SWCU_K_UV_DIFF2 = 6
-    integer(c_int), parameter :: SWCU_K_SW_UPDATE_UV = 7
-    integer(c_int), parameter :: SWCU_K_SW_NEXT_STEP = 8
-    integer(c_int), parameter :: SWCU_K_HH_SHIFT = 9
-    integer(c_int), parameter :: SWCU_K_HH_INIT = 10
-    integer(c_int), parameter :: SWCU_K_CHECK_SSH_ERR = 11
-    integer(c_int), parameter :: SWCU_K_TRAN_DIFF_FLUXES = 12
-    integer(c_int), parameter :: SWCU_K_TRAN_DIFF_TRACER = 13
-    integer(c_int), parameter :: SWCU_K_TRACER_NEXT_STEP = 14
-
-    type, bind(C) :: swcu_dims
-        integer(c_int) :: nx_start, nx_end, ny_start, ny_end
-        integer(c_int) :: bnd_x1, bnd_x2, bnd_y1, bnd_y2
-    end type
-
-    type, bind(C) :: swcu_params
-        integer(c_int) :: full_free_surface, trans_terms, ksw_lat
-        real(c_double) :: time_smooth
-        integer(c_int) :: use_tracers
-        integer(c_int) :: mode
-    end type
-
-    interface
-        function swcu_create(ctx, dims, params, device) bind(C, name="swcu_create") result(rc)
-            import :: c_ptr, c_int, swcu_dims, swcu_params
-            type(c_ptr), intent(out) :: ctx
-            type(swcu_dims), intent(in) :: dims
-            type(swcu_params), intent(in) :: params
-            integer(c_int), value :: device
-            integer(c_int) :: rc
-        end function
-        function swcu_destroy(ctx) bind(C, name="swcu_destroy") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int) :: rc
-        end function
-        function swcu_upload(ctx, field, host) bind(C, name="swcu_upload") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: field
-            type(c_ptr), value :: host
-            integer(c_int) :: rc
-        end function
-        function swcu_download(ctx, field, host) bind(C, name="swcu_download") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: field
-            type(c_ptr), value :: host
-            integer(c_int) :: rc
-        end function
-        function swcu_envoke_hh_init(ctx) bind(C, name="swcu_envoke_hh_init") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int) :: rc
-        end function
-        function swcu_envoke_kernel(ctx, kernel_id, tau) bind(C, name="swcu_envoke_kernel") result(rc)
-            import :: c_ptr, c_int, c_double
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: kernel_id
-            real(c_double), value :: tau
-            integer(c_int) :: rc
-        end function
-        function swcu_envoke_sync(ctx, kernel_id) bind(C, name="swcu_envoke_sync") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: kernel_id
-            integer(c_int) :: rc
-        end function
-        function swcu_step(ctx, tau, nsteps) bind(C, name="swcu_step") result(rc)
-            import :: c_ptr, c_int, c_double
-            type(c_ptr), value :: ctx
-            real(c_double), value :: tau
-            integer(c_int), value :: nsteps
-            integer(c_int) :: rc
-        end function
-        function swcu_peer_export(ctx, blob) bind(C, name="swcu_peer_export") result(rc)
-            import :: c_ptr, c_char, c_int
-            type(c_ptr), value :: ctx
-            character(kind=c_char), intent(out) :: blob(*)
-            integer(c_int) :: rc
-        end function
-        function swcu_peer_attach(ctx, side, blob) bind(C, name="swcu_peer_attach") result(rc)
-            import :: c_ptr, c_char, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: side
-            character(kind=c_char), intent(in) :: blob(*)
-            integer(c_int) :: rc
-        end function
-        function swcu_link(a, b) bind(C, name="swcu_link") result(rc)
-            import :: c_ptr, c_int
-            type(c_ptr), value :: a, b
-            integer(c_int) :: rc
-        end function
-        function swcu_step_group(ctxs, n, tau, nsteps) bind(C, name="swcu_step_group") result(rc)
-            import :: c_ptr, c_int, c_double
-            type(c_ptr), intent(in) :: ctxs(*)
-            integer(c_int), value :: n
-            real(c_double), value :: tau
-            integer(c_int), value :: nsteps
-            integer(c_int) :: rc
-        end function
-        function swcu_device_count() bind(C, name="swcu_device_count") result(n)
-            import :: c_int
-            integer(c_int) :: n
-        end function
-        function swcu_synchronize(ctx, bad_cells) bind(C, name="swcu_synchronize") result(rc)
-            import :: c_ptr, c_int, c_long
-            type(c_ptr), value :: ctx
-            integer(c_long), intent(out) :: bad_cells
-            integer(c_int) :: rc
-        end function
-        function swcu_comm_unique_id(id128) bind(C, name="swcu_comm_unique_id") result(rc)
-            import :: c_char, c_int
-            character(kind=c_char), intent(out) :: id128(128)
-            integer(c_int) :: rc
-        end function
-        function swcu_comm_init(ctx, nranks, rank, id128) bind(C, name="swcu_comm_init") result(rc)
-            import :: c_ptr, c_char, c_int
-            type(c_ptr), value :: ctx
-            integer(c_int), value :: nranks, rank
-            character(kind=c_char), intent(in) :: id128(128)
-            integer(c_int) :: rc
-        end function
-        function swcu_last_error() bind(C, name="swcu_last_error") result(msg)
-            import :: c_ptr
-            type(c_ptr) :: msg
-        end function
-        ! Level A (per-kernel) entry points take CUDA-Fortran device arrays via c_devloc(); their
-        ! interfaces follow the same pattern, e.g.
-        !   swcu_sw_update_ssh_kernel(dims, tau, lu, dx, dy, dxh, dyh, hhu, hhv, sshn, sshp, u, v, stream)
-        ! in the argument order of kernel/shallow_water/vel_ssh.f90:69-70.
-    end interface
-end module swcuda_c_binding
+! (module swcuda_c_binding: fortran/swcuda_c_binding.f90, generated from include/swcuda.h by
+! fortran/gen_bindings.py -- every entry point of the C ABI, the constants and the structs)
 
 
 module shallow_water_interface_cuda_module
@@ -212,10 +55,29 @@ module shallow_water_interface_cuda_module
 
 contains
 
+    ! text of swcu_last_error() as a Fortran string
+    function last_error() result(msg)
+        character(len=:), allocatable :: msg
+        character(kind=c_char), pointer :: p(:)
+        type(c_ptr) :: cp
+        integer :: n
+        cp = swcu_last_error()
+        msg = ''
+        if (.not. c_associated(cp)) return
+        call c_f_pointer(cp, p, [1024])
+        n = 0
+        do while (n < 1024)
+            if (p(n + 1) == c_null_char) exit
+            n = n + 1
+        enddo
+        allocate(character(len=n) :: msg)
+        msg = transfer(p(1:n), msg)
+    end function
+
     subroutine check(rc, what)
         integer(c_int), intent(in) :: rc
         character(*), intent(in) :: what
-        if (rc /= SWCU_OK) call abort_model('swcuda: '//what)      ! shared/errors.f90:30-37
+        if (rc /= SWCU_OK) call abort_model('swcuda: '//what//': '//last_error())      ! shared/errors.f90:30-37
     end subroutine
 
     subroutine up8(k, field, a)
@@ -254,12 +116,21 @@ contains
     subroutine init_device_data_cuda()
         type(swcu_dims) :: d
         type(swcu_params) :: p
-        character(kind=c_char) :: id(128)
-        character(kind=c_char) :: blob_mine(SWCU_PEER_BLOB_BYTES), blob_nbr(SWCU_PEER_BLOB_BYTES)
-        integer :: k, k2, ierr, ndev, node_comm, node_size, side, nbr, to
+        character(kind=c_char), target :: id(128)
+        character(kind=c_char), target :: blob_mine(SWCU_PEER_BLOB_BYTES), blob_nbr(SWCU_PEER_BLOB_BYTES)
+        integer :: k, k2, ierr, ndev, node_comm, node_size, node_rank, side, nbr, to, dev
 
         ndev = max(1, int(swcu_device_count()))
         if (mpp_count > 1 .and. domain%bcount > 1) call abort_model('swcuda: several ranks need one block per rank')
+        ! which GPU: ranks of one node take the node's GPUs in the order of their NODE-LOCAL rank (one block per
+        ! rank); a single rank deals its blocks over the visible GPUs
+        node_rank = 0; node_size = 1; node_comm = mpi_comm_null
+        if (mpp_count > 1) then
+            call mpi_comm_split_type(mpp_cart_comm, mpi_comm_type_shared, 0, mpi_info_null, node_comm, ierr)
+            call mpi_comm_size(node_comm, node_size, ierr)
+            call mpi_comm_rank(node_comm, node_rank, ierr)
+            if (node_size > ndev) call abort_model('swcuda: more ranks on this node than GPUs')
+        endif
         allocate(ctx(domain%bcount))
         p%full_free_surface = full_free_surface; p%trans_terms = trans_terms; p%ksw_lat = ksw_lat
         p%time_smooth = time_smooth; p%use_tracers = use_tracers; p%mode = SWCU_MODE_FUSED
@@ -268,7 +139,9 @@ contains
             d%ny_start = domain%bny_start(k); d%ny_end = domain%bny_end(k)
             d%bnd_x1 = domain%bbnd_x1(k); d%bnd_x2 = domain%bbnd_x2(k)
             d%bnd_y1 = domain%bbnd_y1(k); d%bnd_y2 = domain%bbnd_y2(k)
-            call check(swcu_create(ctx(k), d, p, int(mod(k - 1, ndev), c_int)), 'create')
+            dev = mod(k - 1, ndev)
+            if (mpp_count > 1) dev = mod(node_rank, ndev)
+            call check(swcu_create(ctx(k), d, p, int(dev, c_int)), 'create')
             call up4(k, SWCU_F_LU,  grid_data%lu %block(k)%field); call up4(k, SWCU_F_LUU, grid_data%luu%block(k)%field)
             call up4(k, SWCU_F_LUH, grid_data%luh%block(k)%field); call up4(k, SWCU_F_LCU, grid_data%lcu%block(k)%field)
             call up4(k, SWCU_F_LCV, grid_data%lcv%block(k)%field); call up4(k, SWCU_F_LLU, grid_data%llu%block(k)%field)
@@ -296,13 +169,23 @@ contains
                 if (blocks_touch(k, k2)) call check(swcu_link(ctx(k), ctx(k2)), 'link')
             enddo
         enddo
+        ! The fused step reads the inputs TWO layers outside a block's interior; the reference's arrays are valid
+        ! one layer out (include/swcuda.h, swcu_widen_halos).  Linked blocks fetch the second layer now, ranks
+        ! below, over the communicator.
+        do k = 1, domain%bcount
+            call check(swcu_widen_halos(ctx(k)), 'widen_halos')
+        enddo
         if (mpp_count > 1) then
-            call mpi_comm_split_type(mpp_cart_comm, mpi_comm_type_shared, 0, mpi_info_null, node_comm, ierr)
-            call mpi_comm_size(node_comm, node_size, ierr)
+            ! one NCCL communicator over the y-slab ranks; the id travels over MPI
+            if (mpp_is_master()) call check(swcu_comm_unique_id(c_loc(id)), 'unique_id')
+            call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
+            call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), c_loc(id)), 'comm_init')
+            call check(swcu_widen_halos(ctx(1)), 'widen_halos')
             if (node_size == mpp_count) then
-                ! all ranks on one node: halo rows are stored straight into the neighbours' memory (CUDA IPC),
-                ! the 2048-byte blobs travel once over MPI
-                call check(swcu_peer_export(ctx(1), blob_mine), 'peer_export')
+                ! all ranks on one node: from here on halo rows are stored straight into the neighbours' memory
+                ! (CUDA IPC, fused into the step kernel); the 2048-byte blobs travel once over MPI
+                call check(swcu_comm_destroy(ctx(1)), 'comm_destroy')
+                call check(swcu_peer_export(ctx(1), c_loc(blob_mine)), 'peer_export')
                 do side = 0, 1
                     nbr = mpp_rank - 1 + 2 * side                       ! side 0: rank-1, side 1: rank+1
                     to  = mpp_rank + 1 - 2 * side
@@ -311,13 +194,8 @@ contains
                     call mpi_sendrecv(blob_mine, SWCU_PEER_BLOB_BYTES, mpi_character, to,  side,   &
                                       blob_nbr,  SWCU_PEER_BLOB_BYTES, mpi_character, nbr, side,   &
                                       mpp_cart_comm, mpi_status_ignore, ierr)
-                    if (nbr /= mpi_proc_null) call check(swcu_peer_attach(ctx(1), int(side, c_int), blob_nbr), 'peer_attach')
+                    if (nbr /= mpi_proc_null) call check(swcu_peer_attach(ctx(1), int(side, c_int), c_loc(blob_nbr)), 'peer_attach')
                 enddo
-            else
-                ! several nodes: one NCCL communicator over the y-slab ranks; the id travels over MPI
-                if (mpp_is_master()) call check(swcu_comm_unique_id(id), 'unique_id')
-                call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
-                call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), id), 'comm_init')
             endif
         endif
     end subroutine
@@ -342,7 +220,7 @@ contains
         integer :: k
         integer(c_long) :: bad
         do k = 1, domain%bcount
-            call check(swcu_synchronize(ctx(k), bad), 'SIGFPRE predict error')
+            call check(swcu_synchronize(ctx(k), bad), 'synchronize (SWCU_ERR_BLOWUP = the reference''s SIGFPRE predict error, vel_ssh.f90:57)')
             call check(swcu_download(ctx(k), SWCU_F_SSH, c_loc(ocean_data%ssh%block(k)%field)), 'download')
         enddo
     end subroutine

@@ -299,8 +299,22 @@ int swcu_comm_destroy(swcu_ctx *ctx);
  * get_halo_points_of_block, core/decomposition.f90:94-154, 230-290, widened to nrows). */
 int swcu_halo_plan(const swcu_dims *dims, int nrows, int side, int *send_row, int *recv_row);
 /* One explicit halo exchange of a field (all ranks call it): the analogue of
- * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use. */
+ * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use.  Over a communicator or
+ * in-process links; SWCU_ERR_STATE on a block that uses peer memory (which carries only the step's arrays). */
 int swcu_halo_exchange(swcu_ctx *ctx, int field);
+/* PRECONDITION of SWCU_MODE_FUSED, and the call that establishes it.  The fused step evaluates the depth,
+ * vorticity and stress fields of the cells one layer OUTSIDE a block's interior itself (instead of
+ * exchanging them after every kernel like the reference does), so it reads the inputs -- masks, the nine
+ * metric / Coriolis arrays, hhq_rest, mu, r_diss, RHSx/RHSy and the prognostic arrays -- TWO layers outside
+ * the interior.  The reference fills its block arrays only one layer out (grid_kernels.f90 loops over
+ * nx_start-1 .. nx_end+1; its syncs have width 1, core/decomposition.f90:230-270).  After the initial uploads
+ * and after the neighbours are attached (swcu_comm_init or swcu_link; NOT peer memory -- attach that
+ * afterwards), every block calls swcu_widen_halos once: it exchanges two halo layers of every resident input
+ * (corners included for linked blocks).  Inputs built by swcu_init_grid / uploaded from globally generated
+ * arrays already satisfy the precondition, and the call is then a harmless repetition.  At the GLOBAL
+ * boundary the two outer layers must be land (the reference's masks guarantee a land frame of width 2,
+ * tools/io.f90:49-59), where the values never matter.  No-op in SWCU_MODE_REFERENCE and without neighbours. */
+int swcu_widen_halos(swcu_ctx *ctx);
 
 /* The same y-slab exchange WITHOUT NCCL, for ranks on one node: every rank exports IPC handles of its
  * prognostic buffers (swcu_peer_export fills SWCU_PEER_BLOB_BYTES bytes), the host layer hands each blob

@@ -122,6 +122,7 @@ _SIGNATURES = {
     "swcu_last_error": [],
     "swcu_version": [],
     "swcu_device_count": [],
+    "swcu_widen_halos": [_P],
     "swh_masks": [C.POINTER(SwhBasin), _DIMS] + [_P] * 8,
     "swh_metrics": [C.POINTER(SwhBasin), _DIMS] + [_P] * 9,
     "swh_gaussian": [_DIMS, _P, _P, _D, _I, _I],

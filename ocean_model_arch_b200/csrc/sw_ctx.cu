@@ -140,6 +140,13 @@ int write_value_load()
 
 #define RC(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
+// field-by-field (the struct has padding bytes a Fortran or C caller need not zero)
+bool same_params(const swcu_params &a, const swcu_params &b)
+{
+    return a.full_free_surface == b.full_free_surface && a.trans_terms == b.trans_terms && a.ksw_lat == b.ksw_lat &&
+           a.time_smooth == b.time_smooth && a.use_tracers == b.use_tracers && a.mode == b.mode;
+}
+
 const int kState[6] = {SWCU_F_SSH, SWCU_F_SSHP, SWCU_F_UBRTR, SWCU_F_UBRTRP, SWCU_F_VBRTR, SWCU_F_VBRTRP};
 
 int mask_bit(int field)
@@ -284,7 +291,7 @@ int state_slot(int f)
 template <typename T>
 int exchange_rows(swcu_ctx *c, T *base, int nrows, cudaStream_t st)
 {
-    const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
+    const ncclDataType_t dt = sizeof(T) == 8 ? ncclFloat64 : (sizeof(T) == 4 ? ncclFloat32 : ncclUint8);
     const size_t cnt = (size_t)nrows * c->pitch;
     const int peer[2] = {c->rank - 1, c->rank + 1};
     for (int side = 0; side < 2; ++side) {
@@ -1395,7 +1402,7 @@ int swcu_link(swcu_ctx *a, swcu_ctx *b)
 {
     if (!a || !b || a == b) { set_error("bad argument"); return SWCU_ERR_ARG; }
     if (a->comm || b->comm) { set_error("a block has either in-process links or a communicator"); return SWCU_ERR_STATE; }
-    if (memcmp(&a->p, &b->p, sizeof(swcu_params)) != 0) { set_error("linked blocks need identical parameters"); return SWCU_ERR_ARG; }
+    if (!same_params(a->p, b->p)) { set_error("linked blocks need identical parameters"); return SWCU_ERR_ARG; }
     auto rel = [](int a0, int a1, int b0, int b1, int *out) {
         if (b0 == a1 + 1) { *out = 1; return true; }
         if (b1 + 1 == a0) { *out = -1; return true; }
@@ -1453,7 +1460,7 @@ int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
     for (int i = 0; i < n; ++i) {
         if (!cs[i]) { set_error("null block in the group"); return SWCU_ERR_ARG; }
         if (cs[i]->comm) { set_error("a block with a communicator steps with swcu_step"); return SWCU_ERR_STATE; }
-        if (memcmp(&cs[i]->p, &cs[0]->p, sizeof(swcu_params)) != 0) { set_error("blocks of a group need identical parameters"); return SWCU_ERR_ARG; }
+        if (!same_params(cs[i]->p, cs[0]->p)) { set_error("blocks of a group need identical parameters"); return SWCU_ERR_ARG; }
         for (int j = 0; j < i; ++j) if (cs[j] == cs[i]) { set_error("block listed twice"); return SWCU_ERR_ARG; }
         for (int k = 0; k < 8; ++k) {
             if (!cs[i]->nbr[k]) continue;
@@ -1734,6 +1741,64 @@ int swcu_halo_plan(const swcu_dims *d, int nrows, int side, int *send_row, int *
     return SWCU_OK;
 }
 
+int swcu_widen_halos(swcu_ctx *c)
+{
+    if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
+    if (c->p.mode != SWCU_MODE_FUSED) return SWCU_OK;   // REFERENCE mode keeps the reference's width-1 syncs
+    if (c->peer[0].on || c->peer[1].on) {
+        set_error("swcu_widen_halos runs over a communicator or in-process links: call it before swcu_peer_attach");
+        return SWCU_ERR_STATE;
+    }
+    if (!c->comm && !c->nlinks) return SWCU_OK;          // no neighbours: nothing to widen
+    Use use(c->device);
+    std::vector<double *> p8;
+    std::vector<float *> p4;
+    for (int f = 0; f < SWCU_NF8; ++f) {
+        const bool tracer = c->p.use_tracers && (f == SWCU_F_FF1 || f == SWCU_F_FF1P);
+        if (c->f8[f] && (state_slot(f) >= 0 || f == SWCU_F_HHQ_REST || f == SWCU_F_MU || tracer ||
+                         ((f == SWCU_F_RHSX || f == SWCU_F_RHSY) && c->has_rhs)))
+            p8.push_back(c->f8[f]);
+    }
+    for (int f = SWCU_F_DX; f <= SWCU_F_RLH_S; ++f) if (F4(c, f)) p4.push_back(F4(c, f));
+    if (c->has_rdiss && F4(c, SWCU_F_R_DISS)) p4.push_back(F4(c, SWCU_F_R_DISS));
+    if (c->nlinks) {
+        // position of each plane in the neighbour's lists is the same (same parameters, same residency)
+        int rc = SWCU_OK;
+        for (int k = 0; k < 8 && !rc; ++k) {
+            swcu_ctx *n = c->nbr[k];
+            if (!n) continue;
+            { Use un(n->device); SWCU_CUDA(cudaStreamSynchronize(n->st)); }
+            std::vector<double *> q8;
+            std::vector<float *> q4;
+            for (int f = 0; f < SWCU_NF8; ++f) {
+                const bool tracer = n->p.use_tracers && (f == SWCU_F_FF1 || f == SWCU_F_FF1P);
+                if (n->f8[f] && (state_slot(f) >= 0 || f == SWCU_F_HHQ_REST || f == SWCU_F_MU || tracer ||
+                                 ((f == SWCU_F_RHSX || f == SWCU_F_RHSY) && n->has_rhs)))
+                    q8.push_back(n->f8[f]);
+            }
+            for (int f = SWCU_F_DX; f <= SWCU_F_RLH_S; ++f) if (F4(n, f)) q4.push_back(F4(n, f));
+            if (n->has_rdiss && F4(n, SWCU_F_R_DISS)) q4.push_back(F4(n, SWCU_F_R_DISS));
+            if (q8.size() != p8.size() || q4.size() != p4.size()) { set_error("linked blocks hold different fields"); return SWCU_ERR_STATE; }
+            for (size_t i = 0; i < p8.size() && !rc; ++i) rc = pull_halo<double>(c, k, p8[i], q8[i], 2, c->st);
+            for (size_t i = 0; i < p4.size() && !rc; ++i) rc = pull_halo<float>(c, k, p4[i], q4[i], 2, c->st);
+            if (!rc) rc = pull_halo<unsigned char>(c, k, c->mask, n->mask, 2, c->st);
+        }
+        if (rc) return rc;
+    } else {
+        SWCU_NCCL(g_nccl.GroupStart());
+        int rc = SWCU_OK;
+        for (size_t i = 0; i < p8.size() && !rc; ++i) rc = exchange_rows(c, p8[i], 2, c->st);
+        for (size_t i = 0; i < p4.size() && !rc; ++i) rc = exchange_rows(c, p4[i], 2, c->st);
+        if (!rc) rc = exchange_rows(c, c->mask, 2, c->st);
+        ncclResult_t r = g_nccl.GroupEnd();
+        if (rc) return rc;
+        if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+    }
+    SWCU_CUDA(cudaStreamSynchronize(c->st));
+    c->alt_dirty = true; c->metrics_dirty = true; c->masks_dirty = true;
+    return SWCU_OK;
+}
+
 int swcu_halo_exchange(swcu_ctx *c, int field)
 {
     if (!c) return SWCU_ERR_ARG;
@@ -1747,6 +1812,11 @@ int swcu_halo_exchange(swcu_ctx *c, int field)
         if (is_f4(field)) return pull_blocking<float>(c, hw, 1, [field](const swcu_ctx *x, int) { return x->f4[field - 100]; });
         set_error("unknown field id %d", field);
         return SWCU_ERR_ARG;
+    }
+    if (c->peer[0].on || c->peer[1].on) {
+        set_error("swcu_halo_exchange: this block exchanges halos over peer memory, which carries the prognostic arrays "
+                  "of the step only; exchange set-up fields over a communicator (or swcu_widen_halos) before swcu_peer_attach");
+        return SWCU_ERR_STATE;
     }
     if (!c->comm) return SWCU_OK;
     Use use(c->device);

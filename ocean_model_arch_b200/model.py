@@ -415,6 +415,11 @@ class DeviceBlock:
     def halo_exchange(self, name):
         check(self.L.swcu_halo_exchange(self.h, FIELD_ID[name]))
 
+    def widen_halos(self):
+        """Two halo layers of every resident input from the neighbouring blocks (FUSED-mode precondition when
+        the uploaded arrays are valid one layer out only, like the reference's: include/swcuda.h)."""
+        check(self.L.swcu_widen_halos(self.h))
+
     def link(self, other):
         """Ties this block to a neighbouring block of the same process (side or corner; swcu_link)."""
         check(self.L.swcu_link(self.h, other.h))

@@ -137,3 +137,36 @@ def test_link_errors(swlib, cuda_device):
     blk[0].step(1.0)                              # free again
     for b in blk.values():
         b.close()
+
+
+@pytest.mark.parametrize("layout", [(1, 2), (2, 1), (2, 2)])
+def test_width_one_inputs_need_widen_halos(swlib, cuda_device, layout):
+    """A caller that fills its block arrays like the reference does -- metrics on nx_start-1 .. nx_end+1 only
+    (kernel/service/grid_kernels.f90), state synced with width 1 (core/decomposition.f90:230-270) -- leaves the
+    SECOND layer around each block zero.  The fused step reads that layer; swcu_widen_halos fetches it from
+    the neighbours.  With it the block grid equals the oracle bitwise; without it, it must not (or this test
+    has no teeth)."""
+    nx, ny = 133, 91
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1), mask)
+    o.step(20)
+    bp, sw = model.BasinPar(nx=nx, ny=ny), model.SwPar()
+    results = {}
+    for widen in (True, False):
+        g = model.BlockGridModel(bp, sw, bnx=layout[0], bny=layout[1], mask=mask, keep_mu=True)
+        for blk in g.blocks:
+            inp = model.BlockInputs(bp, sw, blk.dims, mask, keep_mu=True)
+            for name in ("dx", "dy", "dxt", "dyt", "dxh", "dyh", "dxb", "dyb", "rlh_s", "hhq_rest", "mu", "ssh", "sshp"):
+                a = inp.f[name].copy()
+                a[0, :] = 0; a[-1, :] = 0; a[:, 0] = 0; a[:, -1] = 0      # the outermost (second) layer
+                blk.upload(name, a)
+        if widen:
+            for blk in g.blocks:
+                blk.widen_halos()
+        g.step(20)
+        assert g.synchronize() == 0
+        results[widen] = {f: g.get(f) for f in STATE}
+        g.close()
+    for f in STATE:
+        assert np.array_equal(inner(results[True][f]), inner(o.get(f))), (f, layout)
+    assert any(not np.array_equal(results[False][f], results[True][f]) for f in STATE)

@@ -218,3 +218,26 @@ def test_mass_conservation_and_land_at_8192_masked(swlib, cuda_device):
     v0, v1 = (ssh0 * area).sum(), (got["ssh"] * area).sum()
     assert abs(v1 - v0) <= 1e-12 * abs(v0)
     assert not got["ssh"][lu < 0.5].any() and not got["ubrtr"][lu < 0.5].any()
+
+
+def test_config3_masked_basin_4096_against_oracle(swlib, cuda_device):
+    """BASELINE config 3's basin at 4096^2 cells against the oracle in tolerance mode, 10 steps."""
+    n = 4100
+    mask = basins.island_mask(n, n, ndisc=12)
+    o = OracleModel(make_config(n, n, curve_grid=0, bnx=1, bny=16, nthreads=16), mask)
+    m = fast_model(n, n, mask, curve_grid=0, device_init=True)
+    o.step(10); m.step(10)
+    assert m.block.synchronize() == 0
+    check_against(o, m, 1e-13)
+
+
+def test_config4_and_5_physics_1024_against_oracle(swlib, cuda_device):
+    """BASELINE configs 4 / 5 physics (mu = lvisc_2, r_diss = 5e-6, tracers) at 1024^2 in tolerance mode."""
+    n = 1028
+    o = OracleModel(make_config(n, n, curve_grid=0, keep_mu=1, r_diss=5e-6, use_tracers=1, bnx=1, bny=16, nthreads=16), None)
+    m = fast_model(n, n, None, model.SwPar(use_tracers=1), curve_grid=0, keep_mu=True, r_diss=5e-6)
+    o.step(20); m.step(20)
+    assert m.block.synchronize() == 0
+    check_against(o, m, 1e-13)
+    for f in ("ff1", "ff1p"):
+        assert rel(o.get(f), m.get(f)) <= 1e-13, f

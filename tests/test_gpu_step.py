@@ -98,17 +98,21 @@ def test_1000_steps_rel_l2(swlib, cuda_device):
 
 
 def test_fused_equals_reference_sequence_at_2048(swlib, cuda_device):
-    """BASELINE config 2 size (2048^2 cells, too slow for the scalar oracle in a unit test): the two
-    device modes must agree bitwise, and the state must stay finite and bounded."""
+    """BASELINE config 2 (2048^2 cells, flat bottom): both device modes equal the oracle BITWISE at the full
+    size after 20 steps, and the size-independent properties hold."""
     n = 2052
     bp = model.BasinPar(nx=n, ny=n)
     a = model.ShallowWaterModel(bp, mode=MODE_REFERENCE)
     b = model.ShallowWaterModel(bp, mode=MODE_FUSED)
     a.step(20); b.step(20)
     assert a.block.synchronize() == 0 and b.block.synchronize() == 0
+    # ... and the ORACLE at the full size (16 y-slab blocks on the host's threads: seconds)
+    o = OracleModel(make_config(n, n, bnx=1, bny=16, nthreads=16), None)
+    o.step(20)
     for f in STATE:
         x, y = a.get(f), b.get(f)
         assert np.array_equal(x, y), f
+        assert np.array_equal(y, o.get(f)), f
         assert np.isfinite(x).all()
     assert b.block.launches == 20 and a.block.launches == 20 * 11 + 1   # one TMA-tiled launch per step
     # size-independent properties at the full size: mass is conserved (K1 is in flux form; the weight
@@ -439,3 +443,33 @@ def test_external_forcing_rhs(swlib, cuda_device, tiled):
             m.step(7)
             for f in STATE:
                 assert np.array_equal(m.get(f), o.get(f)), (f, it, m.block.mode, tiled)
+
+
+def test_config3_masked_basin_4096_against_oracle(swlib, cuda_device):
+    """BASELINE config 3's basin (synthetic land mask, carthesian) at 4096^2 cells -- the largest size the
+    oracle holds comfortably in host memory -- against the oracle itself: masks, land cells and ssh/u/v
+    BITWISE after 10 steps (one TMA-tiled launch per step, all-land tiles skipped, inputs built on the device)."""
+    n = 4100
+    mask = basins.island_mask(n, n, ndisc=12)
+    o = OracleModel(make_config(n, n, curve_grid=0, bnx=1, bny=16, nthreads=16), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=n, ny=n, curve_grid=0), mask=mask, mode=MODE_FUSED, device_init=True)
+    for f in ("lu", "lcu", "lcv", "luu", "luh", "llu", "llv"):
+        assert np.array_equal(m.get(f), o.get(f)), f
+    o.step(10); m.step(10)
+    assert m.block.synchronize() == 0
+    for f in STATE:
+        assert np.array_equal(m.get(f), o.get(f)), f
+
+
+@pytest.mark.parametrize("mode", [MODE_REFERENCE, MODE_FUSED])
+def test_config4_and_5_physics_1024_against_oracle(swlib, cuda_device, mode):
+    """BASELINE configs 4 and 5 physics (lateral viscosity mu = lvisc_2, bottom friction r_diss = 5e-6, tracer
+    transport) on a 1024^2 carthesian basin against the oracle: BITWISE incl. the tracer after 20 steps."""
+    n = 1028
+    o = OracleModel(make_config(n, n, curve_grid=0, keep_mu=1, r_diss=5e-6, use_tracers=1, bnx=1, bny=16, nthreads=16), None)
+    m = model.ShallowWaterModel(model.BasinPar(nx=n, ny=n, curve_grid=0), model.SwPar(use_tracers=1), mode=mode,
+                                keep_mu=True, r_diss=5e-6)
+    o.step(20); m.step(20)
+    assert m.block.synchronize() == 0
+    for f in STATE + ("ff1", "ff1p"):
+        assert np.array_equal(m.get(f), o.get(f)), (f, mode)
