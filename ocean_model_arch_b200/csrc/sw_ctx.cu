@@ -217,7 +217,7 @@ struct swcu_ctx {
     int tile_variant = 4;
     // tolerance mode (sw_fast.cuh / k_march): "exact" = 0.  The coefficient table depends on tau.
     bool exact = false;
-    double *fc = nullptr;
+    double *fc = nullptr, *ft = nullptr;
     double fc_tau = 0.0;
     bool fc_valid = false;
     int march_warps = 0;                      // SMs x resident warps of k_march on this device
@@ -587,14 +587,18 @@ int fused_main(swcu_ctx *c, double tau)
     a.vort = c->f8[SWCU_F_VORT]; a.str_t = c->f8[SWCU_F_STR_T]; a.str_s = c->f8[SWCU_F_STR_S];
     fill_static_args(c, a);
     a.tab = c->use_tables ? c->tab : nullptr; a.tab_h = c->h;
-    a.fc = nullptr;
+    a.fc = a.ft = nullptr;
     if (!c->exact && c->use_tables) {  // tolerance mode: per-row coefficients (they contain tau)
-        if (!c->fc) RC(dev_alloc(c, (void **)&c->fc, ((size_t)c->h + 4) * swf::FC_STRIDE * sizeof(double)));
+        if (!c->fc) {
+            RC(dev_alloc(c, (void **)&c->fc, ((size_t)c->h + 4) * swf::FC_STRIDE * sizeof(double)));
+            RC(dev_alloc(c, (void **)&c->ft, ((size_t)c->h + 4) * swf::FT_STRIDE * sizeof(double)));
+        }
         if (!c->fc_valid || c->fc_tau != tau) {
-            RC(launch_build_fast(c->tab, c->h, tau, c->fc, c->st));
+            RC(launch_build_fast(c->tab, c->h, tau, c->fc, c->ft, c->st));
             c->fc_valid = true; c->fc_tau = tau; c->launches++;
         }
         a.fc = c->fc;
+        a.ft = c->ft;
     }
     {   // x/tau == x*(1/tau) bitwise when tau is a power of two (exact scaling)
         int ex = 0;
@@ -770,7 +774,16 @@ int fused_main(swcu_ctx *c, double tau)
 // just exchanged: the compute stream already waits on the exchange event)
 int fused_tracer(swcu_ctx *c)
 {
-    RC(launch_tracer(c->g, c->fa, c->g.ny_start, c->g.ny_end, c->st));
+    if (c->fa.fc && march_supported(c->g, c->fa)) {   // tolerance mode: the marching tracer kernel
+        MarchPlan pl;
+        march_plan(c->g, c->g.ny_start, c->g.ny_end, c->march_warps, &pl);
+        if (c->want_land_skip && pl.n0 == c->plan_main.n0 && pl.n1 == c->plan_main.n1 && pl.nbands == c->plan_main.nbands &&
+            !c->plan_main.late_cut)
+            pl.band_land = c->band_land;          // same geometry as the main launch: same all-land bands
+        RC(launch_tracer_march(c->g, c->fa, pl, c->st));
+    } else {
+        RC(launch_tracer(c->g, c->fa, c->g.ny_start, c->g.ny_end, c->st));
+    }
     c->launches++;
     if (c->peer[0].on || c->peer[1].on) {
         const unsigned long long tick = (unsigned long long)c->steps_done + 1;
@@ -1168,7 +1181,7 @@ int swcu_destroy(swcu_ctx *c)
     for (auto &p : c->alt) cudaFree(p);
     for (auto &p : c->alt_ff) cudaFree(p);
     cudaFree(c->mask); cudaFree(c->bad_dev);
-    cudaFree(c->fc); cudaFree(c->band_land);
+    cudaFree(c->fc); cudaFree(c->ft); cudaFree(c->band_land);
     cudaFree(c->tab); cudaFree(c->arr_list_dev); cudaFree(c->nonrow_dev); cudaFree(c->tile_land);
     if (c->bad_host) cudaFreeHost(c->bad_host);
     if (c->ev_bnd) cudaEventDestroy(c->ev_bnd);

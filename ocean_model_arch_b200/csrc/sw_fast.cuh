@@ -149,6 +149,35 @@ SWF_HD void build_fast_row(const double *tab, int h, int r, double tau, double *
     out[FC_RDXH_B] = rdxh;
 }
 
+// Coefficient row of the tracer step (kernel/tracer/leapfrog_tracer.f90:13-170), [row][FT_STRIDE]
+enum FastTracerCoef : int {
+    FT_KU, FT_AREA,      // as FC_KU, FC_AREA
+    FT_AREA_N, FT_KV,
+    FT_DYH, FT_DXH,
+    FT_DYH_RDXT,         // dyh / dxt   (mu_1d of the zonal flux, :63-66)
+    FT_DXH_RDYT,         // dxh / dyt   (meridional flux, :80-83)
+    FT_CTR,              // 2 tau / (dx*dy)   (1 / bp without the thickness, :128)
+    FT_COUNT,
+    FT_STRIDE = 16
+};
+
+SWF_HD void build_tracer_row(const double *tab, int h, int r, double tau, double *out)
+{
+    using namespace swcu;
+    const int rn = r + 1 < h ? r + 1 : r;
+    const double dx = tab[T_DX * h + r], dy = tab[T_DY * h + r];
+    for (int k = 0; k < FT_STRIDE; ++k) out[k] = 0.0;
+    out[FT_KU] = dx * dy * tab[T_RDXT * h + r] * tab[T_RDYH * h + r];
+    out[FT_AREA] = dx * dy;
+    out[FT_AREA_N] = tab[T_DX * h + rn] * tab[T_DY * h + rn];
+    out[FT_KV] = tab[T_RDXH * h + r] * tab[T_RDYT * h + r];
+    out[FT_DYH] = tab[T_DYH * h + r];
+    out[FT_DXH] = tab[T_DXH * h + r];
+    out[FT_DYH_RDXT] = tab[T_DYH * h + r] * tab[T_RDXT * h + r];
+    out[FT_DXH_RDYT] = tab[T_DXH * h + r] * tab[T_RDYT * h + r];
+    out[FT_CTR] = 2.0 * tau / (dx * dy);
+}
+
 // x / dble(lu + lu [+ lu + lu]) with 0/1 masks: a multiplication by 1, 1/2, 1/3, 1/4 (table look-up, no branch)
 #if defined(__CUDACC__)
 static __device__ __constant__ double c_inv_nsea[5] = {1.0, 1.0, 0.5, 1.0 / 3.0, 0.25};
@@ -345,6 +374,49 @@ SWF_HD BOut stage_b(const BCoef &k, unsigned mb, int nsea_u, int nsea_v, double 
     o.up = wu ? r.upf : up_c;
     o.v = wv ? r.vn : v_c;
     o.vp = wv ? r.vpf : vp_c;
+    return o;
+}
+
+
+// ---- tracer step (control/tracer.f90:44-61: fluxes + update + filter) in tolerance arithmetic ---------
+struct TCoef { double ku, area, area_n, kv, dyh, dxh, dyh_rdxt, dxh_rdyt, ctr; };
+
+SWF_HD TCoef load_tcoef(const double *row)
+{
+    TCoef k;
+    k.ku = row[FT_KU]; k.area = row[FT_AREA]; k.area_n = row[FT_AREA_N]; k.kv = row[FT_KV]; k.dyh = row[FT_DYH];
+    k.dxh = row[FT_DXH]; k.dyh_rdxt = row[FT_DYH_RDXT]; k.dxh_rdyt = row[FT_DXH_RDYT]; k.ctr = row[FT_CTR];
+    return k;
+}
+
+struct TFlux { double fx, fy; };
+
+// total fluxes through the east / north face of cell c (leapfrog_tracer.f90:59-90), factor_mu = 1.
+// qm_* = lu ? hhq_rest + ssh_new*ffs : 0: the depths on U / V points are those of the NEW level (what K10 left).
+SWF_HD TFlux tracer_flux(const TCoef &k, unsigned mb, int nsea_u, int nsea_v, double qm_c, double qm_e, double qm_n,
+                         double u_c, double v_c, double mu_c, double mu_e, double mu_n, double ff_c, double ff_e, double ff_n)
+{
+    TFlux f;
+    const double hhu = (qm_c + qm_e) * (k.ku * inv2(nsea_u));
+    const double hhv = mad(qm_c, k.area, qm_n * k.area_n) * (k.kv * inv2(nsea_v));
+    const double gx = mad(0.5 * (mu_c + mu_e) * k.dyh_rdxt, ff_e - ff_c, -(u_c * k.dyh * (0.5 * (ff_c + ff_e))));
+    const double gy = mad(0.5 * (mu_c + mu_n) * k.dxh_rdyt, ff_n - ff_c, -(v_c * k.dxh * (0.5 * (ff_c + ff_n))));
+    f.fx = (mb & LCU) ? hhu * gx : 0.0;
+    f.fy = (mb & LCV) ? hhv * gy : 0.0;
+    return f;
+}
+
+struct TOut { double ffn, ffpf; };
+
+// leapfrog_tracer.f90:128-134 and :163: ffn = (bp0*ffp + rhs) / bp with bp = hhq_rest dx dy / (2 tau),
+// bp0 = (hhq_rest + sshp_new*ffs) dx dy / (2 tau); then the time filter.  qp_c = hhq_rest + sshp_new*ffs.
+SWF_HD TOut tracer_update(const TCoef &k, double ts_half, double h_c, double qp_c, double ff_c, double ffp_c,
+                          double fx_c, double fx_w, double fy_c, double fy_s)
+{
+    TOut o;
+    const double rhs = (fx_c - fx_w) + (fy_c - fy_s);
+    o.ffn = mad(rhs, k.ctr, qp_c * ffp_c) * frcp(h_c);
+    o.ffpf = filt(ff_c, o.ffn, ffp_c, ts_half);
     return o;
 }
 

@@ -25,6 +25,7 @@ struct FusedArgs {
     const double *tab;  // per-row metric tables [T_COUNT][tab_h], nullptr <=> use the 2-D real(4) arrays
     int tab_h;
     const double *fc;   // tolerance mode: per-row coefficient table [tab_h][FC_STRIDE] (sw_fast.cuh), else nullptr
+    const double *ft;   //   ... and the tracer step's [tab_h][FT_STRIDE]
     const unsigned char *mask;
     // one byte per tile of the main (interior / full-range) tiled launch: 1 <=> every output cell of the tile is land, so
     // the tile is skipped (land cells never change; both ping-pong buffers already hold them).
@@ -83,7 +84,8 @@ void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl);
 int march_resident_warps(int device, int minb);  // SMs x resident warps of k_march: the size of one full wave
 int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer = nullptr);
 int march_strip_warps(const Geo &g);  // warps one boundary strip takes (= warp columns)
-int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st);
+int launch_build_fast(const double *tab, int h, double tau, double *fc, double *ft, cudaStream_t st);
+int launch_tracer_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st);
 int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st);
 
 // prep on rows [n0..n1] (columns nx_start-1 .. nx_end+1); update on rows [n0..n1] (columns of S)

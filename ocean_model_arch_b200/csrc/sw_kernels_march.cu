@@ -44,7 +44,7 @@ constexpr int NROW = NARR + 1;  // 256-byte rows per ring slot: the eight arrays
 constexpr int RING = SWCU_RING;  // rows in the per-warp ring
 constexpr int PADW = 2;    // doubles of padding at both ends of a warp's ring (lane -1 / lane 32 reads)
 constexpr int RING_DOUBLES = RING * NROW * 32 + 2 * PADW;
-constexpr int MASK_RING_BYTES = RING * 32;  // one mask byte per lane and ring row
+constexpr int MASK_RING_BYTES = RING * 32 + 16;  // one mask byte per lane and ring row (+ pad: lane 31 reads its east neighbour)
 constexpr size_t MARCH_SMEM = (size_t)MW * (RING_DOUBLES * sizeof(double) + MASK_RING_BYTES);
 
 enum { A_SSH, A_SSHP, A_U, A_UP, A_V, A_VP, A_H, A_MU };
@@ -356,6 +356,109 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
     march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, false>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, -1);
 }
 
+
+// ---- expl_tracer (control/tracer.f90:44-61) for ONE tracer field in tolerance arithmetic, same marching scheme:
+// a warp owns 28 output columns and walks up a band of rows; the new level's ssh, sshp, u, v, the tracer's two
+// levels, hhq_rest and mu arrive through the per-warp ring; the only values that live across rows are the
+// northward flux of the row below and (by shuffle) the eastward flux of the west neighbour.
+enum { T_SSH = 0, T_SSHP = 1, T_U = 2, T_FF = 3, T_V = 4, T_FFP = 5, T_H = 6, T_MU = 7 };
+
+template <bool FFS>
+__global__ void __launch_bounds__(MW * 32, 2)
+k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
+{
+    using namespace swf;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wid = blockIdx.x * MW + wib;
+    if (wid >= pl.nwarps) return;
+    const int band = wid / pl.ncol, col = wid - band * pl.ncol;
+    int bs, be;
+    march_band_rows(pl, band, &bs, &be);
+    if (be < bs) return;
+    if (pl.band_land && pl.band_land[wid]) return;
+
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * RING_DOUBLES + PADW;
+    const unsigned ring_s = smem_addr(ring);
+    const unsigned char *mring = smem_raw + (size_t)MW * RING_DOUBLES * sizeof(double) + (size_t)wib * MASK_RING_BYTES;
+    const unsigned mring_s = smem_addr(mring);
+    const int p = g.pitch, h = g.by2 - g.by1 + 1;
+    const int ax = g.nx_start - 2 - g.bx1 + WOUT * col;
+    const int ac = ax + lane;
+    const int r_first = bs - 1 - g.by1, r_last = be + 1 - g.by1;
+    const int chunk = lane & 15, half = lane >> 4;
+    const int ccol = ax + 2 * chunk;
+    const bool col_ok = ccol + 1 < p;
+    auto issue_row = [&](int r, int slot) {
+        const bool rok = r >= 0 && r <= r_last && r < h;
+        const bool ok = col_ok && rok;
+        const long off = ok ? (long)r * p + ccol : 0;
+#pragma unroll
+        for (int i = 0; i < NARR / 2; ++i) {
+            const double *base = half ? src.in[2 * i + 1] : src.in[2 * i];
+            cp16(ring_s + (unsigned)(((slot * NROW + 2 * i + half) * 32 + 2 * chunk) * sizeof(double)), base + off, ok);
+        }
+        if (half == 0) {
+            if (chunk < FT_STRIDE / 2)
+                cp16(ring_s + (unsigned)(((slot * NROW + NARR) * 32 + 2 * chunk) * sizeof(double)),
+                     a.ft + (rok ? (long)r * FT_STRIDE + 2 * chunk : 0), rok);
+        } else if (chunk < 8) {
+            const bool mok = rok && ax + 4 * chunk + 3 < p;
+            cp4(mring_s + (unsigned)(slot * 32 + 4 * chunk), a.mask + (mok ? (long)r * p + ax + 4 * chunk : 0), mok);
+        }
+        cp_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < RING; ++j) issue_row(r_first + j, j);
+
+    const double ts_half = 0.5 * a.ts;
+    const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
+    double fy_s = 0.0;
+    int s0 = 0, s1 = 1;
+#pragma unroll 2
+    for (int t = bs - 1; t <= be; ++t) {
+        const int rt = t - g.by1;
+        cp_wait<RING - 2>();
+        __syncwarp();
+        const double *r0 = ring + s0 * (NROW * 32) + lane, *r1 = ring + s1 * (NROW * 32) + lane;
+#define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
+        TCoef k;
+        {
+            const double2 *rw = reinterpret_cast<const double2 *>(ring + (s0 * NROW + NARR) * 32);
+            double2 q;
+            q = rw[0]; k.ku = q.x; k.area = q.y;
+            q = rw[1]; k.area_n = q.x; k.kv = q.y;
+            q = rw[2]; k.dyh = q.x; k.dxh = q.y;
+            q = rw[3]; k.dyh_rdxt = q.x; k.dxh_rdyt = q.y;
+            q = rw[4]; k.ctr = q.x;
+        }
+        const unsigned mb0 = mring[s0 * 32 + lane], mbe = mring[s0 * 32 + lane + 1], mb1 = mring[s1 * 32 + lane];
+        const double h0 = AT(r0, T_H, 0);
+        const double qm_c = (mb0 & LU) ? (FFS ? h0 + AT(r0, T_SSH, 0) : h0) : 0.0;
+        const double he = AT(r0, T_H, 1), hn = AT(r1, T_H, 0);
+        const double qm_e = (mbe & LU) ? (FFS ? he + AT(r0, T_SSH, 1) : he) : 0.0;
+        const double qm_n = (mb1 & LU) ? (FFS ? hn + AT(r1, T_SSH, 0) : hn) : 0.0;
+        const int bc = (int)(mb0 & LU);
+        const double ff0 = AT(r0, T_FF, 0);
+        const TFlux f = tracer_flux(k, mb0, bc + (int)(mbe & LU), bc + (int)(mb1 & LU), qm_c, qm_e, qm_n, AT(r0, T_U, 0),
+                                    AT(r0, T_V, 0), AT(r0, T_MU, 0), AT(r0, T_MU, 1), AT(r1, T_MU, 0), ff0, AT(r0, T_FF, 1),
+                                    AT(r1, T_FF, 0));
+        const double fx_w = shfl_up(f.fx);
+        const double ffp0 = AT(r0, T_FFP, 0);
+        const TOut o = tracer_update(k, ts_half, h0, FFS ? h0 + AT(r0, T_SSHP, 0) : h0, ff0, ffp0, f.fx, fx_w, f.fy, fy_s);
+        const bool out = lane_out && t >= bs && (mb0 & LU);
+        const long gc = (long)rt * p + ac;
+        st_if(out, a.ff_o + gc, o.ffn);
+        st_if(out, a.ffp_o + gc, o.ffpf);
+        fy_s = f.fy;
+#undef AT
+        __syncwarp();
+        issue_row(rt + RING, s0);
+        s0 = s1; s1 = s1 + 1 == RING ? 0 : s1 + 1;
+    }
+    cp_wait<0>();
+}
+
 inline int launched(const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -407,7 +510,7 @@ int march_dispatch1(const Geo &g, const FusedArgs &a, const MarchIn &src, const 
 }
 
 // one thread per table row
-__global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, double *__restrict__ fc)
+__global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, double *__restrict__ fc, double *__restrict__ ft)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= h) return;
@@ -415,6 +518,9 @@ __global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, 
     swf::build_fast_row(tab, h, r, tau, row);
 #pragma unroll
     for (int k = 0; k < swf::FC_STRIDE; ++k) fc[(long)r * swf::FC_STRIDE + k] = row[k];
+    swf::build_tracer_row(tab, h, r, tau, row);
+#pragma unroll
+    for (int k = 0; k < swf::FT_STRIDE; ++k) ft[(long)r * swf::FT_STRIDE + k] = row[k];
 }
 
 // band_land[w] = 1 <=> no sea cell among the output cells of warp w's band
@@ -498,9 +604,31 @@ int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStre
     return march_dispatch1<false, false>(g, a, src, pl, peer, st);
 }
 
-int launch_build_fast(const double *tab, int h, double tau, double *fc, cudaStream_t st)
+int launch_tracer_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st)
 {
-    k_build_fast<<<(unsigned)((h + 63) / 64), 64, 0, st>>>(tab, h, tau, fc);
+    if (pl.nwarps < 1 || pl.n1 < pl.n0) return SWCU_OK;
+    static unsigned long long attr_set = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k_tracer_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_tracer_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_tracer_march)");
+        __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
+    }
+    MarchIn src;
+    src.in[T_SSH] = a.ssh_o; src.in[T_SSHP] = a.sshp_o; src.in[T_U] = a.u_o; src.in[T_FF] = a.ff; src.in[T_V] = a.v_o;
+    src.in[T_FFP] = a.ffp; src.in[T_H] = a.h_r; src.in[T_MU] = a.mu;
+    const unsigned grid = (unsigned)((pl.nwarps + MW - 1) / MW);
+    if (a.ffs != 0.0) k_tracer_march<true><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    else k_tracer_march<false><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    return launched("k_tracer_march");
+}
+
+int launch_build_fast(const double *tab, int h, double tau, double *fc, double *ft, cudaStream_t st)
+{
+    k_build_fast<<<(unsigned)((h + 63) / 64), 64, 0, st>>>(tab, h, tau, fc, ft);
     return launched("build_fast");
 }
 

@@ -49,7 +49,7 @@ struct Planes { std::vector<double> rhu, rhv, uh, vh, t, ss, zx, zy, fxp, fyp, f
 template <bool TRANS, bool LAT>
 long steps(int nx, int ny, int nsteps, double tau, double ts, int ffs_i, const unsigned char *mk, const double *fc,
            double *ssh, double *sshp, double *u, double *up, double *v, double *vp, const double *h_r, const double *mu,
-           const double *rhsx, const double *rhsy, const float *rdis)
+           const double *rhsx, const double *rhsy, const float *rdis, const double *ft, double *ff, double *ffp)
 {
     const size_t N = (size_t)nx * ny;
     const double ffs = (double)ffs_i;
@@ -111,6 +111,32 @@ long steps(int nx, int ny, int nsteps, double tau, double ts, int ffs_i, const u
         }
         double *dst[6] = {ssh, sshp, u, up, v, vp};
         for (int k6 = 0; k6 < 6; ++k6) std::memcpy(dst[k6], o[k6].data(), N * sizeof(double));
+        if (ff) {   // expl_tracer on the state just written (control/tracer.f90:44-61)
+            std::vector<double> fx(N, 0.0), fy(N, 0.0), fn(ff, ff + N), fpn(ffp, ffp + N);
+            auto qm = [&](size_t i) { return (mk[i] & LU) ? h_r[i] + ssh[i] * ffs : 0.0; };
+            for (int n = 1; n <= ny - 3; ++n) {
+                const TCoef k = load_tcoef(&ft[(size_t)n * FT_STRIDE]);
+                for (int m = 1; m <= nx - 3; ++m) {
+                    const size_t c = (size_t)n * nx + m, e = c + 1, no = c + nx;
+                    const int b_c = mk[c] & LU, b_e = mk[e] & LU, b_n = mk[no] & LU;
+                    const TFlux f = tracer_flux(k, mk[c], b_c + b_e, b_c + b_n, qm(c), qm(e), qm(no), u[c], v[c], mu[c], mu[e],
+                                                mu[no], ff[c], ff[e], ff[no]);
+                    fx[c] = f.fx; fy[c] = f.fy;
+                }
+            }
+            for (int n = 2; n <= ny - 3; ++n) {
+                const TCoef k = load_tcoef(&ft[(size_t)n * FT_STRIDE]);
+                for (int m = 2; m <= nx - 3; ++m) {
+                    const size_t c = (size_t)n * nx + m;
+                    if (!(mk[c] & LU)) continue;
+                    const TOut t = tracer_update(k, 0.5 * ts, h_r[c], h_r[c] + sshp[c] * ffs, ff[c], ffp[c], fx[c], fx[c - 1],
+                                                 fy[c], fy[c - nx]);
+                    fn[c] = t.ffn; fpn[c] = t.ffpf;
+                }
+            }
+            std::memcpy(ff, fn.data(), N * sizeof(double));
+            std::memcpy(ffp, fpn.data(), N * sizeof(double));
+        }
     }
     return bad;
 }
@@ -120,17 +146,23 @@ long steps(int nx, int ny, int nsteps, double tau, double ts, int ffs_i, const u
 extern "C" {
 
 // metrics: dx dy dxt dyt dxh dyh dxb dyb rlh_s (real(4), (ny, nx)); mk: one byte of mask bits per cell.
+// ff / ffp: one tracer field (NULL without tracers).
 // Returns the number of K11 offenders (sea cells with |ssh| >= 1e4 or NaN), summed over the steps.
 long swf_host_steps(int nx, int ny, int nsteps, double tau, double ts, int ffs, int trans, int lat,
                     const unsigned char *mk, const float *const *metrics,
                     double *ssh, double *sshp, double *u, double *up, double *v, double *vp,
-                    const double *h_r, const double *mu, const double *rhsx, const double *rhsy, const float *rdis)
+                    const double *h_r, const double *mu, const double *rhsx, const double *rhsy, const float *rdis,
+                    double *ff, double *ffp)
 {
     std::vector<double> tab;
     base_table(nx, ny, metrics, tab);
     std::vector<double> fc((size_t)ny * FC_STRIDE);
-    for (int r = 0; r < ny; ++r) build_fast_row(tab.data(), ny, r, tau, &fc[(size_t)r * FC_STRIDE]);
-#define GO(T, L) return steps<T, L>(nx, ny, nsteps, tau, ts, ffs, mk, fc.data(), ssh, sshp, u, up, v, vp, h_r, mu, rhsx, rhsy, rdis)
+    std::vector<double> ft((size_t)ny * FT_STRIDE);
+    for (int r = 0; r < ny; ++r) {
+        build_fast_row(tab.data(), ny, r, tau, &fc[(size_t)r * FC_STRIDE]);
+        build_tracer_row(tab.data(), ny, r, tau, &ft[(size_t)r * FT_STRIDE]);
+    }
+#define GO(T, L) return steps<T, L>(nx, ny, nsteps, tau, ts, ffs, mk, fc.data(), ssh, sshp, u, up, v, vp, h_r, mu, rhsx, rhsy, rdis, ft.data(), ff, ffp)
     if (trans && lat) GO(true, true);
     if (trans) GO(true, false);
     if (lat) GO(false, true);

@@ -46,6 +46,9 @@ class FastHostModel:
         rd = np.ascontiguousarray(oracle.get("r_diss"))
         self.rdis = rd if np.any(rd != 0) else None
         self.bad = 0
+        if cfg.use_tracers > 0:
+            self.state["ff1"] = np.ascontiguousarray(oracle.get("ff1"))
+            self.state["ff1p"] = np.ascontiguousarray(oracle.get("ff1p"))
 
     def step(self, n=1):
         P = C.c_void_p
@@ -57,7 +60,7 @@ class FastHostModel:
             C.c_int(self.nx), C.c_int(self.ny), C.c_int(n), C.c_double(float(cfg.time_step)), C.c_double(cfg.time_smooth),
             C.c_int(cfg.full_free_surface), C.c_int(cfg.trans_terms), C.c_int(cfg.ksw_lat), ptr(self.bits), mets,
             ptr(s["ssh"]), ptr(s["sshp"]), ptr(s["ubrtr"]), ptr(s["ubrtrp"]), ptr(s["vbrtr"]), ptr(s["vbrtrp"]),
-            ptr(self.h_r), ptr(self.mu), P(None), P(None), ptr(self.rdis))
+            ptr(self.h_r), ptr(self.mu), P(None), P(None), ptr(self.rdis), ptr(s.get("ff1")), ptr(s.get("ff1p")))
         return self.bad
 
     def get(self, name):

@@ -75,3 +75,17 @@ def test_random_bathymetry_and_viscosity():
         assert f.step(steps) == 0
         for n in STATE:
             assert rel(o.get(n), f.get(n)) <= 1e-13, (n, steps)
+
+
+def test_tracer_transport_1000_steps():
+    """expl_tracer in tolerance arithmetic (tracer_flux / tracer_update of sw_fast.cuh) with viscosity on."""
+    nx, ny = 100, 77
+    cfg = make_config(nx, ny, keep_mu=1, use_tracers=1)
+    o = OracleModel(cfg, basins.island_mask(nx, ny))
+    f = FastHostModel(o, cfg)
+    o.step(1000)
+    assert f.step(1000) == 0
+    lu = o.get("lu")
+    for n in STATE + ("ff1", "ff1p"):
+        assert rel(o.get(n), f.get(n)) <= 1e-13, (n, rel(o.get(n), f.get(n)))
+    assert np.array_equal(o.get("ff1")[lu < 0.5], f.get("ff1")[lu < 0.5])

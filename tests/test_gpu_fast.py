@@ -241,3 +241,21 @@ def test_config4_and_5_physics_1024_against_oracle(swlib, cuda_device):
     check_against(o, m, 1e-13)
     for f in ("ff1", "ff1p"):
         assert rel(o.get(f), m.get(f)) <= 1e-13, f
+
+
+@pytest.mark.parametrize("shape", [(133, 91), (61, 47), (33, 64)])
+def test_tracer_transport_tolerance_mode(swlib, cuda_device, shape):
+    """k_tracer_march (expl_tracer in one launch after k_march) against the oracle: 300 steps, viscosity on."""
+    nx, ny = shape
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, use_tracers=1), mask)
+    m = fast_model(nx, ny, mask, model.SwPar(use_tracers=1), keep_mu=True)
+    l0 = m.block.launches
+    o.step(300); m.step(300)
+    assert m.block.synchronize() == 0
+    assert m.block.launches - l0 == 2 * 300 + 1
+    check_against(o, m, 1e-13)
+    lu = o.get("lu")
+    for f in ("ff1", "ff1p"):
+        assert rel(o.get(f), m.get(f)) <= 1e-13, f
+        assert np.array_equal(o.get(f)[lu < 0.5], m.get(f)[lu < 0.5]), f
