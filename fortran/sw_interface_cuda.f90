@@ -118,7 +118,7 @@ contains
         type(swcu_params) :: p
         character(kind=c_char), target :: id(128)
         character(kind=c_char), target :: blob_mine(SWCU_PEER_BLOB_BYTES), blob_nbr(SWCU_PEER_BLOB_BYTES)
-        integer :: k, k2, ierr, ndev, node_comm, node_size, node_rank, side, nbr, to, dev
+        integer :: k, k2, t, ierr, ndev, node_comm, node_size, node_rank, side, nbr, to, dev
 
         ndev = max(1, int(swcu_device_count()))
         if (mpp_count > 1 .and. domain%bcount > 1) call abort_model('swcuda: several ranks need one block per rank')
@@ -156,10 +156,14 @@ contains
             call up8(k, SWCU_F_UBRTR,  ocean_data%ubrtr %block(k)%field); call up8(k, SWCU_F_UBRTRP, ocean_data%ubrtrp%block(k)%field)
             call up8(k, SWCU_F_VBRTR,  ocean_data%vbrtr %block(k)%field); call up8(k, SWCU_F_VBRTRP, ocean_data%vbrtrp%block(k)%field)
             call up8(k, SWCU_F_MU,     ocean_data%mu    %block(k)%field)
-            if (use_tracers > 0) then   ! expl_tracer runs inside the step (control/tracer.f90:44-61)
-                if (tracer_num /= 1) call abort_model('swcuda: the device step carries one tracer (tracer_num = 1)')
-                call up8(k, SWCU_F_FF1,  ocean_data%ff1(1) %block(k)%field)
-                call up8(k, SWCU_F_FF1P, ocean_data%ff1p(1)%block(k)%field)
+            if (use_tracers > 0) then   ! expl_tracer runs inside the step (control/tracer.f90:44-61), over all tracers
+                if (tracer_num > 1) call check(swcu_set_option(ctx(k), 'tracer_num'//c_null_char, int(tracer_num, c_int)), 'tracer_num')
+                do t = 1, tracer_num
+                    call check(swcu_set_option(ctx(k), 'tracer_select'//c_null_char, int(t - 1, c_int)), 'tracer_select')
+                    call up8(k, SWCU_F_FF1,  ocean_data%ff1(t) %block(k)%field)
+                    call up8(k, SWCU_F_FF1P, ocean_data%ff1p(t)%block(k)%field)
+                enddo
+                call check(swcu_set_option(ctx(k), 'tracer_select'//c_null_char, 0_c_int), 'tracer_select')
             endif
             call check(swcu_envoke_hh_init(ctx(k)), 'hh_init')
         enddo
@@ -181,8 +185,8 @@ contains
             call mpi_bcast(id, 128, mpi_character, 0, mpp_cart_comm, ierr)
             call check(swcu_comm_init(ctx(1), int(mpp_count, c_int), int(mpp_rank, c_int), c_loc(id)), 'comm_init')
             call check(swcu_widen_halos(ctx(1)), 'widen_halos')
-            if (node_size == mpp_count) then
-                ! all ranks on one node: from here on halo rows are stored straight into the neighbours' memory
+            if (node_size == mpp_count .and. (use_tracers == 0 .or. tracer_num == 1)) then
+                ! all ranks on one node (the peer path carries one tracer): from here on halo rows are stored straight into the neighbours' memory
                 ! (CUDA IPC, fused into the step kernel); the 2048-byte blobs travel once over MPI
                 call check(swcu_comm_destroy(ctx(1)), 'comm_destroy')
                 call check(swcu_peer_export(ctx(1), c_loc(blob_mine)), 'peer_export')

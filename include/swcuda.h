@@ -226,7 +226,17 @@ int swcu_download_to_device(swcu_ctx *ctx, int field, void *dev);
  * land exit before loading anything (flags rebuilt after a mask upload), 0 = compute every tile.
  * "tile_variant": 1..5 selects the tile shape / cells per thread of the tiled kernel (default 4:
  * 32x8 cells, 128 threads, 2 cells per thread, 4 CTAs per SM).  Results are bitwise identical in every
- * combination. */
+ * combination.
+ * "exact": 0 (default; the environment variable SWCU_EXACT=1 changes the default of new contexts) = the fused
+ * step evaluates the reference's scheme with re-associated arithmetic (k_march: products of reciprocals as
+ * per-row coefficients, shared face fluxes, explicit fma) -- ssh / u / v within a relative L2 of 1e-12 of the
+ * reference's CPU path after 1000 steps (measured ~1e-15), masked-out and land cells bit-exact, results
+ * independent of the block decomposition; 1 = every expression in the reference's operation order, bitwise equal
+ * to the CPU path (k_step).  "march_minb": 2 (default) or 3, the register budget variant of k_march.
+ * "tracer_num": number of tracer fields (sw.par line 7, control/tracer.f90:42; default 1; set once after
+ * swcu_create with use_tracers = 1, before uploads of tracers 2..n); "tracer_select": the tracer (0-based) that
+ * the field ids SWCU_F_FF1 / FF1N / FF1P address in uploads, downloads, fills and output records.  A step
+ * advances every tracer.  The peer-memory halo path carries one tracer; several need a communicator. */
 int swcu_set_option(swcu_ctx *ctx, const char *name, int value);
 /* 1 if the last step used the per-row metric tables, 0 if it read the 2-D arrays. */
 int swcu_uses_metric_tables(const swcu_ctx *ctx);

@@ -178,6 +178,12 @@ struct swcu_ctx {
     float *f4[SWCU_NF4] = {};
     double *alt[6] = {};  // FUSED: second copy of the prognostic arrays (ping-pong)
     double *alt_ff[2] = {};  // FUSED + tracers: second copy of ff1, ff1p
+    // tracer_num > 1 (control/tracer.f90:42, core/ocean.f90:91-94): every tracer has its own planes; the ones of
+    // tracer `tr_bound` are those f8[SWCU_F_FF1 / FF1N / FF1P] and alt_ff[] point at; `tr_sel` is the tracer the
+    // caller's uploads / downloads address (option "tracer_select")
+    struct TracerPlanes { double *ff = nullptr, *ffn = nullptr, *ffp = nullptr, *alt[2] = {nullptr, nullptr}; };
+    std::vector<TracerPlanes> tr;
+    int tr_bound = 0, tr_sel = 0;
     unsigned char *mask = nullptr;
     bool alt_dirty = true;
     bool has_rhs = false, has_rdiss = false;
@@ -277,6 +283,27 @@ bool fused_keeps4(const swcu_ctx *c, int f)
     if (f >= SWCU_F_DX && f <= SWCU_F_RLH_S) return true;
     if (f == SWCU_F_R_DISS) return c->has_rdiss;
     return false;
+}
+
+int ntracers(const swcu_ctx *c) { return c->p.use_tracers ? (c->tr.empty() ? 1 : (int)c->tr.size()) : 0; }
+
+// makes tracer k the one the field ids FF1 / FF1N / FF1P and alt_ff address
+void tracer_bind(swcu_ctx *c, int k)
+{
+    if (c->tr.empty() || k == c->tr_bound) return;
+    swcu_ctx::TracerPlanes &cur = c->tr[c->tr_bound];
+    cur.ff = c->f8[SWCU_F_FF1]; cur.ffn = c->f8[SWCU_F_FF1N]; cur.ffp = c->f8[SWCU_F_FF1P];
+    cur.alt[0] = c->alt_ff[0]; cur.alt[1] = c->alt_ff[1];
+    const swcu_ctx::TracerPlanes &nx = c->tr[k];
+    c->f8[SWCU_F_FF1] = nx.ff; c->f8[SWCU_F_FF1N] = nx.ffn; c->f8[SWCU_F_FF1P] = nx.ffp;
+    c->alt_ff[0] = nx.alt[0]; c->alt_ff[1] = nx.alt[1];
+    c->tr_bound = k;
+}
+// the bound tracer's write buffers become its current ones (FUSED ping-pong)
+void tracer_swap(swcu_ctx *c)
+{
+    double *t = c->f8[SWCU_F_FF1]; c->f8[SWCU_F_FF1] = c->alt_ff[0]; c->alt_ff[0] = t;
+    t = c->f8[SWCU_F_FF1P]; c->f8[SWCU_F_FF1P] = c->alt_ff[1]; c->alt_ff[1] = t;
 }
 
 int state_slot(int f)
@@ -453,11 +480,13 @@ int step_reference(swcu_ctx *c, double tau)
     ENVOKE(SWCU_K_SW_NEXT_STEP);
     if (p.full_free_surface > 0) { ENVOKE(SWCU_K_HH_SHIFT); ENVOKE(SWCU_K_HH_INIT); }
     ENVOKE(SWCU_K_CHECK_SSH_ERR);
-    if (p.use_tracers > 0) {
+    for (int k = 0; k < ntracers(c); ++k) {   // control/tracer.f90:42: do k = 1, tracer_num
+        tracer_bind(c, k);
         ENVOKE(SWCU_K_TRAN_DIFF_FLUXES);
         ENVOKE(SWCU_K_TRAN_DIFF_TRACER);
         ENVOKE(SWCU_K_TRACER_NEXT_STEP);
     }
+    tracer_bind(c, c->tr_sel);
     return SWCU_OK;
 }
 
@@ -571,10 +600,12 @@ int fused_main(swcu_ctx *c, double tau)
         for (int i = 0; i < 6; ++i)
             SWCU_CUDA(cudaMemcpyAsync(c->alt[i], c->f8[kState[i]], c->plane * sizeof(double),
                                       cudaMemcpyDeviceToDevice, c->st));
-        if (c->p.use_tracers) {
+        for (int k = 0; k < ntracers(c); ++k) {
+            tracer_bind(c, k);
             SWCU_CUDA(cudaMemcpyAsync(c->alt_ff[0], c->f8[SWCU_F_FF1], c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             SWCU_CUDA(cudaMemcpyAsync(c->alt_ff[1], c->f8[SWCU_F_FF1P], c->plane * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
         }
+        tracer_bind(c, c->tr_sel);
         c->alt_dirty = false;
     }
     FusedArgs &a = c->fa;
@@ -774,6 +805,7 @@ int fused_main(swcu_ctx *c, double tau)
 // just exchanged: the compute stream already waits on the exchange event)
 int fused_tracer(swcu_ctx *c)
 {
+    c->fa.ff = c->f8[SWCU_F_FF1]; c->fa.ffp = c->f8[SWCU_F_FF1P]; c->fa.ff_o = c->alt_ff[0]; c->fa.ffp_o = c->alt_ff[1];
     if (c->fa.fc && march_supported(c->g, c->fa)) {   // tolerance mode: the marching tracer kernel
         MarchPlan pl;
         march_plan(c->g, c->g.ny_start, c->g.ny_end, c->march_warps, &pl);
@@ -803,10 +835,6 @@ int fused_tracer(swcu_ctx *c)
 // the write buffers become the current state
 void fused_swap(swcu_ctx *c)
 {
-    if (c->p.use_tracers) {
-        double *t = c->f8[SWCU_F_FF1]; c->f8[SWCU_F_FF1] = c->alt_ff[0]; c->alt_ff[0] = t;
-        t = c->f8[SWCU_F_FF1P]; c->f8[SWCU_F_FF1P] = c->alt_ff[1]; c->alt_ff[1] = t;
-    }
     for (int i = 0; i < 6; ++i) { double *t = c->f8[kState[i]]; c->f8[kState[i]] = c->alt[i]; c->alt[i] = t; }
     c->cur_set ^= 1;
 }
@@ -814,7 +842,12 @@ void fused_swap(swcu_ctx *c)
 int step_fused(swcu_ctx *c, double tau)
 {
     RC(fused_main(c, tau));
-    if (c->p.use_tracers) RC(fused_tracer(c));
+    for (int k = 0; k < ntracers(c); ++k) {   // control/tracer.f90:42: do k = 1, tracer_num
+        tracer_bind(c, k);
+        RC(fused_tracer(c));
+        tracer_swap(c);
+    }
+    tracer_bind(c, c->tr_sel);
     fused_swap(c);
     return SWCU_OK;
 }
@@ -1175,6 +1208,12 @@ int swcu_destroy(swcu_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto &pl : c->peer)
         for (void *p : pl.opened) cudaIpcCloseMemHandle(p);
+    if (!c->tr.empty()) {
+        tracer_bind(c, 0);
+        for (size_t k = 1; k < c->tr.size(); ++k) {
+            cudaFree(c->tr[k].ff); cudaFree(c->tr[k].ffn); cudaFree(c->tr[k].ffp); cudaFree(c->tr[k].alt[0]); cudaFree(c->tr[k].alt[1]);
+        }
+    }
     cudaFree(c->flags); cudaFree(c->push_count);
     for (auto &p : c->f8) cudaFree(p);
     for (auto &p : c->f4) cudaFree(p);
@@ -1245,6 +1284,39 @@ int swcu_set_option(swcu_ctx *c, const char *name, int value)
         return SWCU_OK;
     }
     if (!strcmp(name, "land_skip")) { c->want_land_skip = value != 0; return SWCU_OK; }
+    if (!strcmp(name, "tracer_num")) {   // sw.par line 7 (configs/sw.f90:41); once, before the tracers are uploaded
+        if (!c->p.use_tracers) { set_error("tracer_num needs use_tracers"); return SWCU_ERR_STATE; }
+        if (value < 1 || value > 64) { set_error("tracer_num must be 1..64"); return SWCU_ERR_ARG; }
+        if (!c->tr.empty() || c->steps_done) { set_error("tracer_num is set once, before the first step"); return SWCU_ERR_STATE; }
+        if (c->peer[0].on || c->peer[1].on) { set_error("the peer-memory halo path carries one tracer: use a communicator"); return SWCU_ERR_STATE; }
+        if (value == 1) return SWCU_OK;
+        Use use(c->device);
+        const bool fused = c->p.mode == SWCU_MODE_FUSED;
+        c->tr.resize((size_t)value);
+        c->tr[0].ff = c->f8[SWCU_F_FF1]; c->tr[0].ffn = c->f8[SWCU_F_FF1N]; c->tr[0].ffp = c->f8[SWCU_F_FF1P];
+        c->tr[0].alt[0] = c->alt_ff[0]; c->tr[0].alt[1] = c->alt_ff[1];
+        for (int k = 1; k < value; ++k) {
+            RC(dev_alloc(c, (void **)&c->tr[k].ff, c->plane * sizeof(double)));
+            RC(dev_alloc(c, (void **)&c->tr[k].ffp, c->plane * sizeof(double)));
+            if (fused) {
+                RC(dev_alloc(c, (void **)&c->tr[k].alt[0], c->plane * sizeof(double)));
+                RC(dev_alloc(c, (void **)&c->tr[k].alt[1], c->plane * sizeof(double)));
+            } else {
+                RC(dev_alloc(c, (void **)&c->tr[k].ffn, c->plane * sizeof(double)));
+            }
+        }
+        SWCU_CUDA(cudaStreamSynchronize(c->st));
+        c->tr_bound = c->tr_sel = 0;
+        return SWCU_OK;
+    }
+    if (!strcmp(name, "tracer_select")) {   // which tracer (0-based) FF1 / FF1N / FF1P address in uploads and downloads
+        if (value < 0 || value >= (ntracers(c) > 0 ? ntracers(c) : 1)) { set_error("tracer_select out of range"); return SWCU_ERR_ARG; }
+        Use use(c->device);
+        SWCU_CUDA(cudaStreamSynchronize(c->st));
+        c->tr_sel = value;
+        tracer_bind(c, value);
+        return SWCU_OK;
+    }
     if (!strcmp(name, "march_minb")) {
         if (value != 2 && value != 3) { set_error("march_minb must be 2 or 3"); return SWCU_ERR_ARG; }
         c->march_minb = value; c->march_warps = 0; c->plan_main.n1 = c->plan_main.n0 - 1; c->masks_dirty = true;
@@ -1473,7 +1545,7 @@ int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
     for (int i = 0; i < n; ++i) {
         if (!cs[i]) { set_error("null block in the group"); return SWCU_ERR_ARG; }
         if (cs[i]->comm) { set_error("a block with a communicator steps with swcu_step"); return SWCU_ERR_STATE; }
-        if (!same_params(cs[i]->p, cs[0]->p)) { set_error("blocks of a group need identical parameters"); return SWCU_ERR_ARG; }
+        if (!same_params(cs[i]->p, cs[0]->p) || ntracers(cs[i]) != ntracers(cs[0])) { set_error("blocks of a group need identical parameters"); return SWCU_ERR_ARG; }
         for (int j = 0; j < i; ++j) if (cs[j] == cs[i]) { set_error("block listed twice"); return SWCU_ERR_ARG; }
         for (int k = 0; k < 8; ++k) {
             if (!cs[i]->nbr[k]) continue;
@@ -1495,11 +1567,12 @@ int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
         if (p.mode == SWCU_MODE_FUSED) {
             for (int i = 0; i < n; ++i) { Use use(cs[i]->device); RC(fused_main(cs[i], tau)); }
             RC(group_pull(cs, n, 6, 2, [](const swcu_ctx *x, int a) { return x->alt[a]; }));
-            if (p.use_tracers) {
-                for (int i = 0; i < n; ++i) { Use use(cs[i]->device); RC(fused_tracer(cs[i])); }
+            for (int k = 0; k < ntracers(cs[0]); ++k) {
+                for (int i = 0; i < n; ++i) { Use use(cs[i]->device); tracer_bind(cs[i], k); RC(fused_tracer(cs[i])); }
                 RC(group_pull(cs, n, 2, 2, [](const swcu_ctx *x, int a) { return x->alt_ff[a]; }));
+                for (int i = 0; i < n; ++i) tracer_swap(cs[i]);
             }
-            for (int i = 0; i < n; ++i) fused_swap(cs[i]);
+            for (int i = 0; i < n; ++i) { tracer_bind(cs[i], cs[i]->tr_sel); fused_swap(cs[i]); }
         } else {  // control/shallow_water/shallow_water.f90:22-94, then control/tracer.f90:44-61
             RC(envoke(SWCU_K_SW_UPDATE_SSH));
             if (p.full_free_surface > 0) RC(envoke(SWCU_K_HH_UPDATE));
@@ -1509,11 +1582,13 @@ int swcu_step_group(swcu_ctx *const *cs, int n, double tau, int nsteps)
             RC(envoke(SWCU_K_SW_NEXT_STEP));
             if (p.full_free_surface > 0) { RC(envoke(SWCU_K_HH_SHIFT)); RC(envoke(SWCU_K_HH_INIT)); }
             RC(envoke(SWCU_K_CHECK_SSH_ERR));
-            if (p.use_tracers > 0) {
+            for (int k = 0; k < ntracers(cs[0]); ++k) {
+                for (int i = 0; i < n; ++i) tracer_bind(cs[i], k);
                 RC(envoke(SWCU_K_TRAN_DIFF_FLUXES));
                 RC(envoke(SWCU_K_TRAN_DIFF_TRACER));
                 RC(envoke(SWCU_K_TRACER_NEXT_STEP));
             }
+            for (int i = 0; i < n; ++i) tracer_bind(cs[i], cs[i]->tr_sel);
         }
         for (int i = 0; i < n; ++i) cs[i]->steps_done++;
     }
@@ -1677,6 +1752,7 @@ int swcu_peer_export(swcu_ctx *c, void *blob)
 {
     if (!c || !blob) { set_error("null argument"); return SWCU_ERR_ARG; }
     if (c->p.mode != SWCU_MODE_FUSED) { set_error("the peer-memory halo path needs SWCU_MODE_FUSED"); return SWCU_ERR_STATE; }
+    if (ntracers(c) > 1) { set_error("the peer-memory halo path carries one tracer: use a communicator"); return SWCU_ERR_STATE; }
     Use use(c->device);
     PeerBlob b;
     memset(&b, 0, sizeof(b));
@@ -1766,12 +1842,18 @@ int swcu_widen_halos(swcu_ctx *c)
     Use use(c->device);
     std::vector<double *> p8;
     std::vector<float *> p4;
+    auto other_tracers = [](swcu_ctx *x, std::vector<double *> &v) {   // tracers 1 .. n-1 (tracer 0 is bound here)
+        for (size_t k = 1; k < x->tr.size(); ++k) { v.push_back(x->tr[k].ff); v.push_back(x->tr[k].ffp); }
+    };
+    tracer_bind(c, 0);
+    for (int k = 0; k < 8; ++k) if (c->nbr[k]) tracer_bind(c->nbr[k], 0);
     for (int f = 0; f < SWCU_NF8; ++f) {
         const bool tracer = c->p.use_tracers && (f == SWCU_F_FF1 || f == SWCU_F_FF1P);
         if (c->f8[f] && (state_slot(f) >= 0 || f == SWCU_F_HHQ_REST || f == SWCU_F_MU || tracer ||
                          ((f == SWCU_F_RHSX || f == SWCU_F_RHSY) && c->has_rhs)))
             p8.push_back(c->f8[f]);
     }
+    other_tracers(c, p8);
     for (int f = SWCU_F_DX; f <= SWCU_F_RLH_S; ++f) if (F4(c, f)) p4.push_back(F4(c, f));
     if (c->has_rdiss && F4(c, SWCU_F_R_DISS)) p4.push_back(F4(c, SWCU_F_R_DISS));
     if (c->nlinks) {
@@ -1789,6 +1871,7 @@ int swcu_widen_halos(swcu_ctx *c)
                                  ((f == SWCU_F_RHSX || f == SWCU_F_RHSY) && n->has_rhs)))
                     q8.push_back(n->f8[f]);
             }
+            other_tracers(n, q8);
             for (int f = SWCU_F_DX; f <= SWCU_F_RLH_S; ++f) if (F4(n, f)) q4.push_back(F4(n, f));
             if (n->has_rdiss && F4(n, SWCU_F_R_DISS)) q4.push_back(F4(n, SWCU_F_R_DISS));
             if (q8.size() != p8.size() || q4.size() != p4.size()) { set_error("linked blocks hold different fields"); return SWCU_ERR_STATE; }
@@ -1808,6 +1891,8 @@ int swcu_widen_halos(swcu_ctx *c)
         if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
     }
     SWCU_CUDA(cudaStreamSynchronize(c->st));
+    tracer_bind(c, c->tr_sel);
+    for (int k = 0; k < 8; ++k) if (c->nbr[k]) tracer_bind(c->nbr[k], c->nbr[k]->tr_sel);
     c->alt_dirty = true; c->metrics_dirty = true; c->masks_dirty = true;
     return SWCU_OK;
 }

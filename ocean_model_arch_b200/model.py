@@ -246,6 +246,12 @@ class DeviceBlock:
         self.h = h
         if exact is not None and mode == MODE_FUSED:
             self.set_option("exact", 1 if exact else 0)
+        if sw.use_tracers > 0 and sw.tracer_num > 1:       # core/ocean.f90:91-94: ff1(tracer_num)
+            self.set_option("tracer_num", int(sw.tracer_num))
+
+    def select_tracer(self, k):
+        """Tracer k (0-based) becomes the one the names ff1 / ff1n / ff1p address."""
+        self.set_option("tracer_select", int(k))
 
     def upload(self, name, arr):
         want = np.float64 if name in F8_NAMES else np.float32
@@ -348,6 +354,12 @@ class DeviceBlock:
             if name == "r_diss" and not arr.any():
                 continue  # the reference never assigns r_diss (core/ocean.f90:32)
             self.upload(name, arr)
+        for k in range(1, self.sw.tracer_num if self.sw.use_tracers > 0 else 1):   # init_data.f90:82-86: every tracer
+            self.select_tracer(k)                                                 # starts from the same Gaussian
+            for name in ("ff1", "ff1n", "ff1p"):
+                self.upload(name, inp.f[name])
+        if self.sw.use_tracers > 0 and self.sw.tracer_num > 1:
+            self.select_tracer(0)
         self.hh_init()
 
     def hh_init(self):

@@ -473,3 +473,39 @@ def test_config4_and_5_physics_1024_against_oracle(swlib, cuda_device, mode):
     assert m.block.synchronize() == 0
     for f in STATE + ("ff1", "ff1p"):
         assert np.array_equal(m.get(f), o.get(f)), (f, mode)
+
+
+@pytest.mark.parametrize("mode,exact", [(MODE_REFERENCE, True), (MODE_FUSED, True), (MODE_FUSED, False)])
+def test_several_tracers(swlib, cuda_device, mode, exact):
+    """tracer_num = 3 (control/tracer.f90:42 loops over ff1(k); core/ocean.f90:91-94).  The tracer equation is
+    linear and homogeneous in ff, so a field scaled by a power of two must stay the oracle's tracer times that
+    power BITWISE (scaling by 2^k is exact) -- in the tolerance arithmetic too, against its own first tracer."""
+    nx, ny = 133, 91
+    mask = basins.island_mask(nx, ny)
+    o = OracleModel(make_config(nx, ny, keep_mu=1, use_tracers=1), mask)
+    m = model.ShallowWaterModel(model.BasinPar(nx=nx, ny=ny), model.SwPar(use_tracers=1, tracer_num=3), mask=mask,
+                                mode=mode, keep_mu=True, exact=exact)
+    ff = m.get("ff1")
+    for k, scale in ((1, 4.0), (2, 0.125)):
+        m.block.select_tracer(k)
+        for f in ("ff1", "ff1n", "ff1p"):
+            m.block.upload(f, ff * scale)
+    m.block.select_tracer(0)
+    l0 = m.block.launches
+    o.step(40); m.step(40)
+    assert m.block.synchronize() == 0
+    first = {f: m.get(f) for f in ("ff1", "ff1p")}
+    for f in ("ff1", "ff1p"):
+        if exact:
+            assert np.array_equal(first[f], o.get(f)), f
+        else:
+            assert np.linalg.norm(first[f] - o.get(f)) <= 1e-13 * np.linalg.norm(o.get(f)), f
+    for k, scale in ((1, 4.0), (2, 0.125)):
+        m.block.select_tracer(k)
+        for f in ("ff1", "ff1p"):
+            assert np.array_equal(m.get(f), first[f] * scale), (f, k)
+    if mode == MODE_FUSED:
+        assert m.block.launches - l0 == 40 * (1 + 3) + (0 if exact else 1)
+    for f in STATE:     # the dynamics do not notice the extra tracers
+        if exact:
+            assert np.array_equal(m.get(f), o.get(f)), f
