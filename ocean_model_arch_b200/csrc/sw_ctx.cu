@@ -243,9 +243,10 @@ namespace {
 
 int dev_alloc(swcu_ctx *c, void **ptr, size_t bytes)
 {
-    SWCU_CUDA(cudaMalloc(ptr, bytes));
-    SWCU_CUDA(cudaMemsetAsync(*ptr, 0, bytes, c->st));
-    c->bytes += (long)bytes;
+    // + slack: k_march's bulk copies read whole 256-byte row segments that may run past the last row's pitch
+    SWCU_CUDA(cudaMalloc(ptr, bytes + 512));
+    SWCU_CUDA(cudaMemsetAsync(*ptr, 0, bytes + 512, c->st));
+    c->bytes += (long)bytes + 512;
     return SWCU_OK;
 }
 int alloc8(swcu_ctx *c, int f)
@@ -661,10 +662,35 @@ int fused_main(swcu_ctx *c, double tau)
     const bool fused_push = march && peers && (ne - ns + 1) >= 4;
     const int sides = fused_push ? (lo ? 1 : 0) + (hi ? 2 : 0) : 0;
     if (march && (c->masks_dirty || c->plan_main.n0 != main0 || c->plan_main.n1 != main1 || c->plan_sides != sides)) {
-        // geometry of the main launch and the all-land flags of its bands
-        march_plan(g, main0, main1, c->march_warps, &c->plan_main);
+        // Geometry of the main launch and the all-land flags of its bands.  First with short bands (128 rows): if
+        // enough of them are all land (they cost nothing and the block scheduler balances the rest) keep that;
+        // otherwise one wave of equal bands, which has the least warm-up and no tail.
+        int fine_rows = 128;
+        if (const char *e = getenv("SWCU_BAND_ROWS")) fine_rows = atoi(e);
+        bool fine = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool try_fine = pass == 0 && c->want_land_skip && fine_rows > 0 && (main1 - main0 + 1) >= 4 * fine_rows;
+            if (pass == 0 && !try_fine) continue;
+            march_plan(g, main0, main1, c->march_warps, &c->plan_main, try_fine ? fine_rows : 0);
+            const size_t need = (size_t)(c->plan_main.nwarps > 0 ? c->plan_main.nwarps : 1);
+            if (need > c->band_land_cap) {
+                if (c->band_land) { cudaFree(c->band_land); c->bytes -= (long)c->band_land_cap; }
+                c->band_land = nullptr; c->band_land_cap = 0;
+                RC(dev_alloc(c, (void **)&c->band_land, need));
+                c->band_land_cap = need;
+            }
+            if (main1 < main0) break;
+            SWCU_CUDA(cudaMemsetAsync(c->nonrow_dev, 0, sizeof(int), c->st));
+            RC(launch_band_land(g, c->mask, c->plan_main, c->band_land, c->nonrow_dev, c->st));
+            if (try_fine) {
+                int nland = 0;
+                SWCU_CUDA(cudaMemcpyAsync(&nland, c->nonrow_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+                SWCU_CUDA(cudaStreamSynchronize(c->st));
+                if (nland * 10 >= c->plan_main.nwarps) { fine = true; break; }   // >= 10 % of the bands are all land
+            } else break;
+        }
         c->plan_sides = sides;
-        if (sides) {
+        if (sides && !fine) {
             // the lowest / highest band's warps do the boundary strip first (about ten row iterations incl. the
             // second ring start-up): those bands get that much less to do
             int cut = 10;
@@ -676,14 +702,6 @@ int fused_main(swcu_ctx *c, double tau)
                 c->plan_main.late_cut = cut;
             }
         }
-        const size_t need = (size_t)(c->plan_main.nwarps > 0 ? c->plan_main.nwarps : 1);
-        if (need > c->band_land_cap) {
-            if (c->band_land) { cudaFree(c->band_land); c->bytes -= (long)c->band_land_cap; }
-            c->band_land = nullptr; c->band_land_cap = 0;
-            RC(dev_alloc(c, (void **)&c->band_land, need));
-            c->band_land_cap = need;
-        }
-        if (main1 >= main0) RC(launch_band_land(g, c->mask, c->plan_main, c->band_land, c->st));
         c->masks_dirty = false;
     }
     if (tiled && (c->masks_dirty || c->tile_land_n0 != main0 || c->tile_land_n1 != main1)) {
@@ -808,10 +826,12 @@ int fused_tracer(swcu_ctx *c)
     c->fa.ff = c->f8[SWCU_F_FF1]; c->fa.ffp = c->f8[SWCU_F_FF1P]; c->fa.ff_o = c->alt_ff[0]; c->fa.ffp_o = c->alt_ff[1];
     if (c->fa.fc && march_supported(c->g, c->fa)) {   // tolerance mode: the marching tracer kernel
         MarchPlan pl;
-        march_plan(c->g, c->g.ny_start, c->g.ny_end, c->march_warps, &pl);
-        if (c->want_land_skip && pl.n0 == c->plan_main.n0 && pl.n1 == c->plan_main.n1 && pl.nbands == c->plan_main.nbands &&
-            !c->plan_main.late_cut)
-            pl.band_land = c->band_land;          // same geometry as the main launch: same all-land bands
+        if (c->plan_main.n0 == c->g.ny_start && c->plan_main.n1 == c->g.ny_end && !c->plan_main.late_cut) {
+            pl = c->plan_main;                    // same rows as the main launch: same bands, same all-land flags
+            pl.band_land = c->want_land_skip ? c->band_land : nullptr;
+        } else {
+            march_plan(c->g, c->g.ny_start, c->g.ny_end, c->march_warps, &pl);
+        }
         RC(launch_tracer_march(c->g, c->fa, pl, c->st));
     } else {
         RC(launch_tracer(c->g, c->fa, c->g.ny_start, c->g.ny_end, c->st));

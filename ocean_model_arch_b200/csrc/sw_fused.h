@@ -80,13 +80,14 @@ __host__ __device__ inline void march_band_rows(const MarchPlan &pl, int band, i
     *be = march_band_start(pl, band + 1) - 1;
 }
 bool march_supported(const Geo &g, const FusedArgs &a);
-void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl);
+void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl, int band_rows = 0);
 int march_resident_warps(int device, int minb);  // SMs x resident warps of k_march: the size of one full wave
 int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer = nullptr);
 int march_strip_warps(const Geo &g);  // warps one boundary strip takes (= warp columns)
 int launch_build_fast(const double *tab, int h, double tau, double *fc, double *ft, cudaStream_t st);
 int launch_tracer_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st);
-int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st);
+int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, int *nland_dev,
+                     cudaStream_t st);
 
 // prep on rows [n0..n1] (columns nx_start-1 .. nx_end+1); update on rows [n0..n1] (columns of S)
 int launch_prep(const Geo &g, const FusedArgs &a, int n0, int n1, cudaStream_t st);

@@ -44,8 +44,21 @@ constexpr int NROW = NARR + 1;  // 256-byte rows per ring slot: the eight arrays
 constexpr int RING = SWCU_RING;  // rows in the per-warp ring
 constexpr int PADW = 2;    // doubles of padding at both ends of a warp's ring (lane -1 / lane 32 reads)
 constexpr int RING_DOUBLES = RING * NROW * 32 + 2 * PADW;
-constexpr int MASK_RING_BYTES = RING * 32 + 16;  // one mask byte per lane and ring row (+ pad: lane 31 reads its east neighbour)
-constexpr size_t MARCH_SMEM = (size_t)MW * (RING_DOUBLES * sizeof(double) + MASK_RING_BYTES);
+#ifndef SWCU_RING_TMA
+#define SWCU_RING_TMA 0
+#endif
+// Ring fill: 0 (default) = per-lane 16-byte cp.async (LDGSTS); 1 = TMA bulk copies (cp.async.bulk, UBLKCP in SASS)
+// issued by one lane and completing on one mbarrier per ring row.  Measured at 2048^2 on one B200 (same box, same
+// call): 0.1315 ms with cp.async, 0.1346 ms with bulk copies -- one lane issuing ten copies per row serialises
+// what 32 lanes issue in five instructions, and every row pays an mbarrier try_wait.  The bulk path cannot zero-fill, so it reads
+// whole 256-byte row segments that may run up to 31 columns past the pitch (into the next row, or into the
+// slack every plane is allocated with): those columns only ever feed discarded lanes.
+constexpr bool RING_TMA = SWCU_RING_TMA != 0;
+constexpr int MASK_ROW = RING_TMA ? 48 : 32;   // bytes per mask ring row (bulk copies start 16-byte aligned)
+constexpr int MASK_RING_BYTES = RING * MASK_ROW + 16;  // (+ pad: lane 31 reads its east neighbour)
+constexpr int MBAR_BYTES = RING * 8;
+constexpr size_t MARCH_SMEM = (size_t)MW * (RING_DOUBLES * sizeof(double) + MASK_RING_BYTES + MBAR_BYTES);
+constexpr unsigned ROW_TX_BYTES = NROW * 256 + MASK_ROW;
 
 enum { A_SSH, A_SSHP, A_U, A_UP, A_V, A_VP, A_H, A_MU };
 
@@ -61,6 +74,28 @@ __device__ __forceinline__ void cp4(unsigned dst, const void *src, bool valid)
     const unsigned sz = valid ? 4u : 0u;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+// ---- TMA bulk copies + mbarrier (one per ring row and warp)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -102,17 +137,34 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
     const unsigned ring_s = smem_addr(ring);
     const unsigned char *mring = smem_raw + (size_t)MW * RING_DOUBLES * sizeof(double) + (size_t)wib * MASK_RING_BYTES;
     const unsigned mring_s = smem_addr(mring);
+    const unsigned bars = smem_addr(smem_raw + (size_t)MW * (RING_DOUBLES * sizeof(double) + MASK_RING_BYTES) + (size_t)wib * MBAR_BYTES);
     const int p = g.pitch, h = g.by2 - g.by1 + 1;
     const int ax = g.nx_start - 2 - g.bx1 + WOUT * col;  // array column of lane 0
     const int ac = ax + lane;                            // my array column
     const int r_first = bs - 2 - g.by1;                  // array row of the first staged row (>= 0)
     const int r_last = be + 2 - g.by1;                   // last row anybody reads (<= h-1)
+    const int mo = RING_TMA ? (ax & 15) : 0;             // my mask byte within a mask ring row: mo + lane
 
-    // ---- ring fill: one array row = 16 chunks of 16 B; a warp instruction moves two arrays' rows
+    // ---- ring fill.  TMA: lane 0 arms the row's mbarrier and issues ten bulk copies (eight array rows, the
+    // coefficient row, the mask bytes).  cp.async: one array row = 16 chunks of 16 B, a warp instruction
+    // moves two arrays' rows.
     const int chunk = lane & 15, half = lane >> 4;
     const int ccol = ax + 2 * chunk;
     const bool col_ok = ccol + 1 < p;
     auto issue_row = [&](int r, int slot) {  // r: array row
+        if (RING_TMA) {
+            if (lane == 0 && r <= r_last) {
+                const unsigned bar = bars + 8u * slot;
+                mbar_expect(bar, ROW_TX_BYTES);
+                const long off = (long)r * p + ax;
+                const unsigned dst = ring_s + (unsigned)(slot * NROW * 256);
+#pragma unroll
+                for (int k = 0; k < NARR; ++k) bulk_g2s(dst + 256u * k, src.in[k] + off, 256u, bar);
+                bulk_g2s(dst + 256u * NARR, a.fc + (long)r * swf::FC_STRIDE, 256u, bar);
+                bulk_g2s(mring_s + (unsigned)(slot * MASK_ROW), a.mask + (long)r * p + (ax & ~15), (unsigned)MASK_ROW, bar);
+            }
+            return;
+        }
         const bool ok = col_ok && r >= 0 && r <= r_last && r < h;
         const long off = ok ? (long)r * p + ccol : 0;
 #pragma unroll
@@ -131,6 +183,16 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
         }
         cp_commit();
     };
+    // row `j` (counted from r_first) of the ring has landed: j-th use of slot j % RING
+    auto wait_row = [&](int slot, int use) {
+        if (RING_TMA) mbar_wait(bars + 8u * slot, (unsigned)use & 1u);
+    };
+    if (RING_TMA) {
+        if (lane == 0)
+            for (int j = 0; j < RING; ++j) mbar_init(bars + 8u * j, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
 #define RNG(slot, arr, dl) ring[((slot) * NROW + (arr)) * 32 + lane + (dl)]
 
 #pragma unroll
@@ -154,9 +216,10 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
     float rd_n = 0.0f;
 
     // prologue: what stage A of row bs-1 needs from row bs-1 (slot 1)
-    cp_wait<RING - 2>();
+    if (RING_TMA) { wait_row(0, 0); wait_row(1, 0); }
+    else cp_wait<RING - 2>();
     __syncwarp();
-    mb1 = mring[1 * 32 + lane];
+    mb1 = mring[1 * MASK_ROW + mo + lane];
     {
         const double h1 = RNG(1, A_H, 0);
         S[0].q = FFS ? h1 + RNG(1, A_SSH, 0) : h1;
@@ -184,10 +247,11 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
                      *r2 = ring + s2i * (NROW * 32) + lane;
 #define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
 
-        cp_wait<RING - 3>();  // row b+2 has landed (my copies) ...
-        __syncwarp();         // ... and everybody else's
+        if (RING_TMA) wait_row(s2i, (rb - r_first + 2) / RING);   // row b+2 has landed
+        else cp_wait<RING - 3>();                                  // ... (my copies) ...
+        __syncwarp();                                              // ... and everybody else's
 
-        const unsigned mb2 = mring[s2i * 32 + lane];
+        const unsigned mb2 = mring[s2i * MASK_ROW + mo + lane];
         // coefficient rows from the ring (uniform addresses: broadcast 16-byte loads; pair k = columns 2k, 2k+1)
         ACoef ka;
         BCoef kb;
@@ -524,7 +588,8 @@ __global__ void k_build_fast(const double *__restrict__ tab, int h, double tau, 
 }
 
 // band_land[w] = 1 <=> no sea cell among the output cells of warp w's band
-__global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, MarchPlan pl, unsigned char *__restrict__ out)
+__global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, MarchPlan pl, unsigned char *__restrict__ out,
+                            int *__restrict__ nland)
 {
     const int w = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
     if (w >= pl.ncol * pl.nbands) return;
@@ -536,7 +601,10 @@ __global__ void k_band_land(Geo g, const unsigned char *__restrict__ mask, March
     if (lane < WOUT && m <= g.nx_end)
         for (int n = bs; n <= be; ++n) any |= mask[ix(g, m, n)] & MB_LU;
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) out[w] = any ? 0 : 1;
+    if (lane == 0) {
+        out[w] = any ? 0 : 1;
+        if (!any && nland) atomicAdd(nland, 1);
+    }
 }
 
 }  // namespace
@@ -550,17 +618,23 @@ bool march_supported(const Geo &g, const FusedArgs &a)
            g.pitch % 4 == 0 && g.ny_start - 2 >= g.by1 && g.ny_end + 2 <= g.by2;
 }
 
-// Warp columns x bands for rows [n0..n1]: as many bands as keep every warp resident at once
-// (max_warps = SMs x resident warps), but bands of at least min_rows rows (each band pays 2 warm-up rows).
-void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl)
+// Warp columns x bands for rows [n0..n1].  band_rows = 0: as many bands as keep every warp resident at once
+// (max_warps = SMs x resident warps; one wave, equal work), but bands of at least 16 rows (each band pays 2
+// warm-up rows).  band_rows > 0: bands of about that many rows -- more warps than fit at once, the hardware
+// block scheduler balances them; for basins with land, where all-land bands cost nothing.
+void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl, int band_rows)
 {
     pl->n0 = n0; pl->n1 = n1;
     pl->ncol = (g.nx_end - g.nx_start + WOUT) / WOUT;
     const int nrows = n1 - n0 + 1;
     const int min_rows = 16;
-    int nb = max_warps / (pl->ncol > 0 ? pl->ncol : 1);
-    if (nb < 1) nb = 1;
-    if (nb > (nrows + min_rows - 1) / min_rows) nb = (nrows + min_rows - 1) / min_rows;
+    int nb;
+    if (band_rows > 0) {
+        nb = (nrows + band_rows - 1) / band_rows;
+    } else {
+        nb = max_warps / (pl->ncol > 0 ? pl->ncol : 1);
+        if (nb > (nrows + min_rows - 1) / min_rows) nb = (nrows + min_rows - 1) / min_rows;
+    }
     if (nb < 1) nb = 1;
     pl->nbands = nb;
     pl->nwarps = pl->ncol * nb;
@@ -632,11 +706,12 @@ int launch_build_fast(const double *tab, int h, double tau, double *fc, double *
     return launched("build_fast");
 }
 
-int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, cudaStream_t st)
+int launch_band_land(const Geo &g, const unsigned char *mask, const MarchPlan &pl, unsigned char *out, int *nland_dev,
+                     cudaStream_t st)
 {
     const int n = pl.ncol * pl.nbands;
     if (n < 1 || pl.n1 < pl.n0) return SWCU_OK;
-    k_band_land<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(g, mask, pl, out);
+    k_band_land<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(g, mask, pl, out, nland_dev);
     return launched("band_land");
 }
 
