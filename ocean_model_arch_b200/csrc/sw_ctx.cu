@@ -227,6 +227,7 @@ struct swcu_ctx {
     double fc_tau = 0.0;
     bool fc_valid = false;
     int march_warps = 0;                      // SMs x resident warps of k_march on this device
+    int tracer_warps = 0;                     //   ... of k_tracer_march
     int march_minb = 2;
     MarchPlan plan_main = {0, -1, 0, 0, 0, 0, 0, 0, nullptr, 2};
     int plan_sides = -1;
@@ -826,11 +827,13 @@ int fused_tracer(swcu_ctx *c)
     c->fa.ff = c->f8[SWCU_F_FF1]; c->fa.ffp = c->f8[SWCU_F_FF1P]; c->fa.ff_o = c->alt_ff[0]; c->fa.ffp_o = c->alt_ff[1];
     if (c->fa.fc && march_supported(c->g, c->fa)) {   // tolerance mode: the marching tracer kernel
         MarchPlan pl;
-        if (c->plan_main.n0 == c->g.ny_start && c->plan_main.n1 == c->g.ny_end && !c->plan_main.late_cut) {
-            pl = c->plan_main;                    // same rows as the main launch: same bands, same all-land flags
+        if (!c->tracer_warps) c->tracer_warps = march_tracer_resident_warps(c->device);
+        if (c->plan_main.n0 == c->g.ny_start && c->plan_main.n1 == c->g.ny_end && !c->plan_main.late_cut &&
+            c->plan_main.nwarps > c->march_warps) {
+            pl = c->plan_main;                    // short bands over the same rows: same bands, same all-land flags
             pl.band_land = c->want_land_skip ? c->band_land : nullptr;
         } else {
-            march_plan(c->g, c->g.ny_start, c->g.ny_end, c->march_warps, &pl);
+            march_plan(c->g, c->g.ny_start, c->g.ny_end, c->tracer_warps, &pl);   // one wave of this kernel
         }
         RC(launch_tracer_march(c->g, c->fa, pl, c->st));
     } else {

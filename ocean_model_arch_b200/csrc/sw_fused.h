@@ -82,6 +82,7 @@ __host__ __device__ inline void march_band_rows(const MarchPlan &pl, int band, i
 bool march_supported(const Geo &g, const FusedArgs &a);
 void march_plan(const Geo &g, int n0, int n1, int max_warps, MarchPlan *pl, int band_rows = 0);
 int march_resident_warps(int device, int minb);  // SMs x resident warps of k_march: the size of one full wave
+int march_tracer_resident_warps(int device);
 int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer = nullptr);
 int march_strip_warps(const Geo &g);  // warps one boundary strip takes (= warp columns)
 int launch_build_fast(const double *tab, int h, double tau, double *fc, double *ft, cudaStream_t st);

@@ -425,10 +425,14 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
 // a warp owns 28 output columns and walks up a band of rows; the new level's ssh, sshp, u, v, the tracer's two
 // levels, hhq_rest and mu arrive through the per-warp ring; the only values that live across rows are the
 // northward flux of the row below and (by shuffle) the eastward flux of the west neighbour.
+constexpr int TR_RING = 6;   // rows t, t+1 live + four in flight: small enough for three CTAs per SM
+constexpr int TR_RING_DOUBLES = TR_RING * NROW * 32 + 2 * PADW;
+constexpr int TR_MASK_RING_BYTES = TR_RING * 32 + 16;
+constexpr size_t TRACER_SMEM = (size_t)MW * (TR_RING_DOUBLES * sizeof(double) + TR_MASK_RING_BYTES);
 enum { T_SSH = 0, T_SSHP = 1, T_U = 2, T_FF = 3, T_V = 4, T_FFP = 5, T_H = 6, T_MU = 7 };
 
 template <bool FFS>
-__global__ void __launch_bounds__(MW * 32, 2)
+__global__ void __launch_bounds__(MW * 32, 3)
 k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 {
     using namespace swf;
@@ -442,9 +446,9 @@ k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
     if (be < bs) return;
     if (pl.band_land && pl.band_land[wid]) return;
 
-    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * RING_DOUBLES + PADW;
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)wib * TR_RING_DOUBLES + PADW;
     const unsigned ring_s = smem_addr(ring);
-    const unsigned char *mring = smem_raw + (size_t)MW * RING_DOUBLES * sizeof(double) + (size_t)wib * MASK_RING_BYTES;
+    const unsigned char *mring = smem_raw + (size_t)MW * TR_RING_DOUBLES * sizeof(double) + (size_t)wib * TR_MASK_RING_BYTES;
     const unsigned mring_s = smem_addr(mring);
     const int p = g.pitch, h = g.by2 - g.by1 + 1;
     const int ax = g.nx_start - 2 - g.bx1 + WOUT * col;
@@ -473,7 +477,7 @@ k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
         cp_commit();
     };
 #pragma unroll
-    for (int j = 0; j < RING; ++j) issue_row(r_first + j, j);
+    for (int j = 0; j < TR_RING; ++j) issue_row(r_first + j, j);
 
     const double ts_half = 0.5 * a.ts;
     const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
@@ -482,7 +486,7 @@ k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
 #pragma unroll 2
     for (int t = bs - 1; t <= be; ++t) {
         const int rt = t - g.by1;
-        cp_wait<RING - 2>();
+        cp_wait<TR_RING - 2>();
         __syncwarp();
         const double *r0 = ring + s0 * (NROW * 32) + lane, *r1 = ring + s1 * (NROW * 32) + lane;
 #define AT(rp, arr, dl) (rp)[(arr) * 32 + (dl)]
@@ -517,8 +521,8 @@ k_tracer_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl)
         fy_s = f.fy;
 #undef AT
         __syncwarp();
-        issue_row(rt + RING, s0);
-        s0 = s1; s1 = s1 + 1 == RING ? 0 : s1 + 1;
+        issue_row(rt + TR_RING, s0);
+        s0 = s1; s1 = s1 + 1 == TR_RING ? 0 : s1 + 1;
     }
     cp_wait<0>();
 }
@@ -661,6 +665,17 @@ int march_resident_warps(int device, int minb)
     return sms * per_sm * MW;
 }
 
+// SMs x resident warps of k_tracer_march (fewer registers than k_march: three CTAs per SM where shared memory allows)
+int march_tracer_resident_warps(int device)
+{
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148 * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_tracer_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACER_SMEM);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tracer_march<true>, MW * 32, TRACER_SMEM);
+    if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+    return sms * per_sm * MW;
+}
+
 int march_strip_warps(const Geo &g) { return (g.nx_end - g.nx_start + WOUT) / WOUT; }
 
 int launch_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, cudaStream_t st, const MarchPeer *peer_in)
@@ -685,9 +700,9 @@ int launch_tracer_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, c
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(k_tracer_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_tracer_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACER_SMEM);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_tracer_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MARCH_SMEM);
+            e = cudaFuncSetAttribute(k_tracer_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACER_SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_tracer_march)");
         __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
     }
@@ -695,8 +710,8 @@ int launch_tracer_march(const Geo &g, const FusedArgs &a, const MarchPlan &pl, c
     src.in[T_SSH] = a.ssh_o; src.in[T_SSHP] = a.sshp_o; src.in[T_U] = a.u_o; src.in[T_FF] = a.ff; src.in[T_V] = a.v_o;
     src.in[T_FFP] = a.ffp; src.in[T_H] = a.h_r; src.in[T_MU] = a.mu;
     const unsigned grid = (unsigned)((pl.nwarps + MW - 1) / MW);
-    if (a.ffs != 0.0) k_tracer_march<true><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
-    else k_tracer_march<false><<<grid, MW * 32, MARCH_SMEM, st>>>(g, a, src, pl);
+    if (a.ffs != 0.0) k_tracer_march<true><<<grid, MW * 32, TRACER_SMEM, st>>>(g, a, src, pl);
+    else k_tracer_march<false><<<grid, MW * 32, TRACER_SMEM, st>>>(g, a, src, pl);
     return launched("k_tracer_march");
 }
 
