@@ -692,14 +692,14 @@ int fused_main(swcu_ctx *c, double tau)
         }
         c->plan_sides = sides;
         if (sides && !fine) {
-            // the lowest / highest band's warps do the boundary strip first (about ten row iterations incl. the
-            // second ring start-up): those bands get that much less to do
-            int cut = 10;
+            // the strip kernel runs concurrently and holds ncol / 4 CTA slots per side for the first microseconds:
+            // the CTAs of the main launch that are scheduled last (its last band per side) start that much later
+            // and get that many rows less to do
+            int cut = 24;   // measured at 2048^2 per GPU, 2 GPUs: cut 0 0.1279, 8 0.1288, 16 0.1223, 24 0.1189 ms (1 GPU: 0.1145)
             if (const char *e = getenv("SWCU_LATE_CUT")) cut = atoi(e);
-            const int nb = c->plan_main.nbands;
-            if ((main1 - main0 + 1) / nb > 4 * cut && (nb > 1 || sides != 3)) {
-                c->plan_main.late_lo = (sides & 1) ? 1 : 0;
-                c->plan_main.late_hi = (sides & 2) ? 1 : 0;
+            const int nb = c->plan_main.nbands, late = (sides & 1) + ((sides >> 1) & 1);
+            if (cut > 0 && nb > late && (main1 - main0 + 1) / nb > 2 * cut) {
+                c->plan_main.late_hi = late;
                 c->plan_main.late_cut = cut;
             }
         }
@@ -753,13 +753,20 @@ int fused_main(swcu_ctx *c, double tau)
     if (!lo && !hi) {
         RC(rows(ns, ne, c->st));
     } else if (fused_push) {
+        // ---- tolerance arithmetic over peer memory.  Two launches per step that write disjoint rows and run
+        // concurrently: the lean k_march over the interior rows on the compute stream, and the strip kernel
+        // (k_march<PEER>: boundary rows + their push into the neighbours' halo rows + the step counter) on the
+        // high-priority stream.  No stream ever waits for a neighbour: the strip warps do, inside the kernel.
         const unsigned long long tick = (unsigned long long)c->steps_done + 1;
-        // my write buffers may be written by the neighbours from here on (everything that read them has been
-        // issued before on this stream): two stream-ordered stores into their flag words, no kernel
         RC(write_value_load());
-        for (int side = 0; side < 2; ++side) {
-            if (!c->peer[side].on) continue;
-            CUresult r = g_write_value((CUstream)c->st, (CUdeviceptr)(c->peer[side].flags + (side == 0 ? 3 : 2)), tick, 0);
+        int dbg = 0;
+        if (const char *e = getenv("SWCU_PEER_DBG")) dbg = atoi(e);
+        // everything that read my write buffers (the previous step, an upload's copy) is on the compute stream
+        SWCU_CUDA(cudaEventRecord(c->ev_start, c->st));
+        SWCU_CUDA(cudaStreamWaitEvent(c->bnd_st, c->ev_start, 0));
+        for (int side = 0; side < 2; ++side) {   // "my write buffers may be written from here on"
+            if (!c->peer[side].on || (dbg & 4)) continue;
+            CUresult r = g_write_value((CUstream)c->bnd_st, (CUdeviceptr)(c->peer[side].flags + (side == 0 ? 3 : 2)), tick, 0);
             if (r != CUDA_SUCCESS) { set_error("cuStreamWriteValue64 failed with %d", (int)r); return SWCU_ERR_CUDA; }
         }
         MarchPeer mp;
@@ -774,18 +781,28 @@ int fused_main(swcu_ctx *c, double tau)
             for (int k = 0; k < 6; ++k) mp.out[side][k] = pl.set[wset][k] + shift;
             mp.ready[side] = pl.flags + (side == 0 ? 1 : 0);   // I am the block above my lower neighbour
             mp.free_[side] = c->flags + 2 + side;
+            mp.ready_in[side] = c->flags + side;
             mp.count[side] = c->push_count + 2 + side;
         }
         mp.tick = tick;
-        if (const char *e = getenv("SWCU_PEER_DBG")) mp.dbg = atoi(e);
-        MarchPlan pl = c->plan_main;
-        pl.band_land = c->want_land_skip ? c->band_land : nullptr;
-        pl.minb = c->march_minb;
-        RC(prof_mark(c, 1, true, c->st));
-        RC(launch_march(g, a, pl, c->st, &mp));
-        RC(prof_mark(c, 1, false, c->st));
+        mp.dbg = dbg;
+        // strips: band 0's warps take the lower strip, the last band's the upper one; no band rows
+        MarchPlan sp;
+        march_plan(g, ns, ns - 1, c->march_warps, &sp);
+        sp.nbands = (lo && hi) ? 2 : 1;
+        sp.nwarps = sp.ncol * sp.nbands;
+        RC(prof_mark(c, 1, true, c->bnd_st));
+        RC(launch_march(g, a, sp, c->bnd_st, &mp));
+        RC(prof_mark(c, 1, false, c->bnd_st));
+        SWCU_CUDA(cudaEventRecord(c->ev_bnd, c->bnd_st));
         c->launches++;
-        RC(peer_wait(c, c->st, 0, tick));   // my halo rows of the new state have arrived
+        // interior
+        RC(rows(main0, main1, c->st));
+        // whatever comes next on the compute stream (the next step, a tracer kernel, a download) sees the strips
+        SWCU_CUDA(cudaStreamWaitEvent(c->st, c->ev_bnd, 0));
+        // ... and only a tracer kernel, which reads the new state's halo rows right now, needs the neighbours' rows
+        // on the stream; the next step's strip warps wait for them in the kernel
+        if (c->p.use_tracers && !(dbg & 4)) RC(peer_wait(c, c->st, 0, tick));
     } else {
         // The two boundary strips (the rows each neighbour needs) run on a high-priority stream
         // concurrently with the interior update; their completion releases the exchange on a second
@@ -793,6 +810,7 @@ int fused_main(swcu_ctx *c, double tau)
         // compute stream joins before the next step.
         const unsigned long long tick = (unsigned long long)c->steps_done + 1;
         int i0 = ns, i1 = ne;
+        if (peers && tick > 1) RC(peer_wait(c, c->st, 0, tick - 1));   // (a no-op unless the previous step ran fused)
         if (peers)   // my write buffers may be written by the neighbours from here on (alt sync is done)
             RC(launch_signal(lo ? c->peer[0].flags + 3 : nullptr, hi ? c->peer[1].flags + 2 : nullptr, tick, c->st));
         SWCU_CUDA(cudaEventRecord(c->ev_start, c->st));
@@ -1423,6 +1441,8 @@ int swcu_synchronize(swcu_ctx *c, long *bad_cells)
 {
     if (!c) { set_error("null ctx"); return SWCU_ERR_ARG; }
     Use use(c->device);
+    if ((c->peer[0].on || c->peer[1].on) && c->steps_done > 0)   // the neighbours' rows of the last step have landed
+        RC(peer_wait(c, c->st, 0, (unsigned long long)c->steps_done));
     SWCU_CUDA(cudaMemcpyAsync(c->bad_host, c->bad_dev, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     SWCU_CUDA(cudaMemsetAsync(c->bad_dev, 0, sizeof(int), c->st));
     SWCU_CUDA(cudaStreamSynchronize(c->st));
@@ -1837,6 +1857,10 @@ int swcu_peer_attach(swcu_ctx *c, int side, const void *blob)
     pl.flags = (unsigned long long *)f;
     pl.by1 = b.by1;
     pl.on = true;
+    {   // the halo rows towards this neighbour are valid as of the steps taken so far
+        const unsigned long long v = (unsigned long long)c->steps_done;
+        SWCU_CUDA(cudaMemcpy(c->flags + side, &v, sizeof(v), cudaMemcpyHostToDevice));
+    }
     return SWCU_OK;
 }
 

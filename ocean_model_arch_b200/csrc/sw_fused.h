@@ -46,22 +46,24 @@ struct FusedArgs {
 struct MarchPlan {
     int n0, n1;
     int ncol, nbands, nwarps;        // nwarps = ncol * nbands
-    // Fused halo push (MarchPeer): the warps of band 0 first work on the lower boundary strip, those of band
-    // nbands-1 on the upper one; such a band is `late_cut` rows shorter than the others (a strip costs about
-    // that many row iterations), so all warps of the launch finish together.
+    // The last `late_hi` bands are `late_cut` rows shorter than the others: with a fused halo push the strip
+    // kernel runs concurrently and holds a few CTA slots for the first microseconds, so the CTAs of the main
+    // launch that are scheduled last start that much later.  (late_lo: the same for band 0; unused.)
     int late_lo, late_hi, late_cut;
     const unsigned char *band_land;  // [nwarps]: 1 <=> the warp's output cells are all land (skipped), or nullptr
     int minb;                        // register budget variant: sized for 2 or 3 CTAs per SM
 };
 // Halo push fused into k_march (neighbouring blocks in other processes of the node, peer-mapped memory):
-// the warps of the lowest / highest band first compute the boundary strip of their side, store it ALSO into
-// that neighbour's halo rows over NVLink, and the last of them publishes `tick` in the neighbour's "halo
-// ready" word; then they march their own band like everybody else.
+// a small k_march<PEER> launch on the high-priority stream, concurrent with the lean main launch (disjoint rows):
+// its warps wait for the neighbour's rows of the previous step, compute the boundary strip of their side, store
+// it ALSO into that neighbour's halo rows over NVLink, and the last of them publishes `tick` in the neighbour's
+// "halo ready" word.
 // Side 0 = the block below (rank-1), 1 = the block above.  A side is active iff out[side][0] != nullptr.
 struct MarchPeer {
     int lo0, lo1, hi0, hi1;              // rows of the lower / upper strip (inclusive; empty if x1 < x0)
     double *out[2][6];                   // the neighbours' write planes, shifted so that MY element index applies
     unsigned long long *ready[2];        // the neighbours' "halo ready" words (peer-mapped)
+    const unsigned long long *ready_in[2];  // MY "halo ready" words: the neighbour's push of step tick-1 has landed
     const unsigned long long *free_[2];  // my "your rows in my write buffers may be overwritten" words
     unsigned long long tick;
     unsigned *count[2];                  // strip-warp counters (zero between launches)
@@ -71,8 +73,9 @@ struct MarchPeer {
 __host__ __device__ inline int march_band_start(const MarchPlan &pl, int band)
 {
     const long R = (long)(pl.n1 - pl.n0 + 1) + (long)pl.late_cut * (pl.late_lo + pl.late_hi);
+    const int first_late = pl.nbands - pl.late_hi;
     return pl.n0 + (int)((long)band * R / pl.nbands) - (band >= 1 ? pl.late_lo * pl.late_cut : 0) -
-           (band == pl.nbands ? pl.late_hi * pl.late_cut : 0);
+           (band > first_late ? (band - first_late) * pl.late_cut : 0);
 }
 __host__ __device__ inline void march_band_rows(const MarchPlan &pl, int band, int *bs, int *be)
 {

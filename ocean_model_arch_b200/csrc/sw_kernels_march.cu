@@ -5,11 +5,11 @@
 // side) and marches up a band of rows, one row per iteration.  There is no CTA-wide barrier and no
 // shared-memory tile of intermediates:
 //   - the eight input arrays (ssh, sshp, u, up, v, vp, hhq_rest, mu), the mask bytes and the row's
-//     coefficients arrive through a per-warp ring of RING rows in shared memory, filled with cp.async
+//     coefficients arrive through a per-warp ring of RING (6) rows in shared memory, filled with cp.async
 //     (LDGSTS, zero-filled outside the array) RING-3 rows ahead of their use: all of a warp's HBM reads
 //     are in flight while it computes, and nothing in the loop waits for a global load;
-//   - every input value is read from the ring ONCE when it enters the 3-row stencil window and then
-//     rotates through registers (row b+2 -> b+1 -> b);
+//   - raw inputs are read from the ring where they are needed (rows b .. b+2 stay there for the whole
+//     iteration); only computed values live across rows;
 //   - stage A (depths, volume fluxes, stresses, vorticity: the quantities a U/V/H/T point owns) is
 //     evaluated one row ahead of stage B; its results rotate through registers the same way and reach
 //     the east / west neighbours by warp shuffles;
@@ -35,7 +35,7 @@ namespace {
 #define SWCU_MW 4
 #endif
 #ifndef SWCU_RING
-#define SWCU_RING 8
+#define SWCU_RING 6   // measured: 4 rows 0.1259, 5 rows 0.1235, 6 rows 0.1200, 8 rows 0.1231 ms (2048^2, same box)
 #endif
 constexpr int MW = SWCU_MW;  // warps per CTA (the CTA is only a container: warps never synchronise with each other)
 constexpr int WOUT = 28;   // output columns per warp
@@ -44,6 +44,12 @@ constexpr int NROW = NARR + 1;  // 256-byte rows per ring slot: the eight arrays
 constexpr int RING = SWCU_RING;  // rows in the per-warp ring
 constexpr int PADW = 2;    // doubles of padding at both ends of a warp's ring (lane -1 / lane 32 reads)
 constexpr int RING_DOUBLES = RING * NROW * 32 + 2 * PADW;
+// Two-row unroll of the marching loop (computed values then swap between two register banks without copies).
+// Measured SLOWER than the plain loop that copies ~18 doubles per row (0.1294 vs 0.1175 ms at 2048^2, same box):
+// the unrolled body is 13 KB of SASS, the plain one 7 KB.  Kept as an option.
+#ifndef SWCU_MARCH_UNROLL2
+#define SWCU_MARCH_UNROLL2 0
+#endif
 #ifndef SWCU_RING_TMA
 #define SWCU_RING_TMA 0
 #endif
@@ -125,8 +131,9 @@ struct MarchIn {
     const double *in[NARR];  // ssh sshp u up v vp hhq_rest mu
 };
 
-// One warp's march over rows [bs..be] of warp column `col`.  PUSH: the warp works on a boundary strip and
-// stores its results also into the neighbour's halo rows (side 0 = below, 1 = above).
+// One warp's march over rows [bs..be] of warp column `col`.  side >= 0: the rows are a boundary strip whose
+// results are stored also into that neighbour's halo rows (side 0 = below, 1 = above) -- a rare, warp-uniform
+// branch that fetches the neighbour's plane pointers from the parameter bank only when it is taken.
 template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, bool PUSH>
 __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, const MarchIn &src, const MarchPeer &peer,
                                            unsigned char *smem_raw, const int lane, const int wib, const int col,
@@ -232,14 +239,6 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
     const double ts_half = 0.5 * a.ts;
     const bool lane_out = lane >= 2 && lane < 2 + WOUT && (g.bx1 + ac) <= g.nx_end;
     int s0 = 0, s1i = 1, s2i = 2;  // ring slots of rows b, b+1, b+2
-
-    // strip warps: the neighbour's planes (nullptr for band warps)
-    double *p_ssh = nullptr, *p_sshp = nullptr, *p_u = nullptr, *p_up = nullptr, *p_v = nullptr, *p_vp = nullptr;
-    if (PUSH) {
-        p_ssh = side ? peer.out[1][0] : peer.out[0][0]; p_sshp = side ? peer.out[1][1] : peer.out[0][1];
-        p_u = side ? peer.out[1][2] : peer.out[0][2]; p_up = side ? peer.out[1][3] : peer.out[0][3];
-        p_v = side ? peer.out[1][4] : peer.out[0][4]; p_vp = side ? peer.out[1][5] : peer.out[0][5];
-    }
 
     auto row = [&](const int b, Bank &X, Bank &Y) {
         const int rb = b - g.by1;  // array row of b
@@ -348,7 +347,7 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
         st_if(wu, a.u_o + gc, o.un); st_if(wu, a.up_o + gc, o.upf);
         st_if(wv, a.v_o + gc, o.vn); st_if(wv, a.vp_o + gc, o.vpf);
         if (sea && ssh_bad(o.sshn)) atomicAdd(a.bad, 1);  // K11
-        if (PUSH && b >= bs) {
+        if (PUSH && side >= 0 && b >= bs) {
             // boundary strip: the same cells go straight into the neighbour's halo rows (NVLink stores).  The
             // neighbour must have declared those rows of its write buffers free for this step.
             if (b == bs && !(peer.dbg & 1)) {
@@ -360,9 +359,10 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
                 __threadfence_system();
             }
             const bool ps = !(peer.dbg & 2);
-            st_if(sea && ps, p_ssh + gc, o.sshn); st_if(sea && ps, p_sshp + gc, o.sshpf);
-            st_if(wu && ps, p_u + gc, o.un); st_if(wu && ps, p_up + gc, o.upf);
-            st_if(wv && ps, p_v + gc, o.vn); st_if(wv && ps, p_vp + gc, o.vpf);
+            double *const *po = side ? peer.out[1] : peer.out[0];
+            st_if(sea && ps, po[0] + gc, o.sshn); st_if(sea && ps, po[1] + gc, o.sshpf);
+            st_if(wu && ps, po[2] + gc, o.un); st_if(wu && ps, po[3] + gc, o.upf);
+            st_if(wv && ps, po[4] + gc, o.vn); st_if(wv && ps, po[5] + gc, o.vpf);
         }
 #undef AT
 
@@ -372,17 +372,32 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
         s0 = s1i; s1i = s2i; s2i = s2i + 1 == RING ? 0 : s2i + 1;
         mb0 = mb1; mb1 = mb2; lue0 = lue1; lue1 = lue2;
     };
+#if SWCU_MARCH_UNROLL2
     for (int b = bs - 2; b <= be; b += 2) {
         row(b, S[0], S[1]);
         if (b + 1 <= be) row(b + 1, S[1], S[0]);
     }
+#else
+#pragma unroll 1
+    for (int b = bs - 2; b <= be; ++b) {
+        row(b, S[0], S[1]);
+        const AOut keep = S[0].A;   // row b's stage A is still the "row below" of the next iteration
+        S[0] = S[1];
+        S[1].A = keep;
+    }
+#endif
     cp_wait<0>();
 #undef RNG
 }
 
 // MINB = CTAs per SM the register budget is sized for (2: 255 registers, 8 warps per SM; 3: 168 registers,
-// 12 warps per SM and a few spilled values).  PEER: the launch carries boundary strips whose results are also
-// pushed into the neighbours' memory (the edge bands' warps run the PUSH body first, then everybody the lean one).
+// 12 warps per SM).
+// PEER = false: the lean kernel -- every warp marches its band, nothing else is compiled in (a segment loop
+// around the march body costs every warp 4.5 %, a rarely taken push branch inside it another 4 %: measured).
+// PEER = true: the boundary-strip kernel of the fused halo push -- the warps of band 0 work on the lower strip,
+// those of band nbands-1 on the upper one (both if there is one band): wait for the neighbour's rows of the
+// previous step, compute the strip, store it also into the neighbour's halo rows, publish the step counter.
+// It runs concurrently with the lean kernel (other stream, disjoint rows).
 template <bool TRANS, bool LAT, bool FFS, bool HAS_RHS, bool HAS_RDISS, int MINB, bool PEER>
 __global__ void __launch_bounds__(MW * 32, MINB)
 k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
@@ -391,33 +406,40 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wid = blockIdx.x * MW + wib;
     if (wid >= pl.nwarps) return;
-    const int w = wid;
-    const int band = w / pl.ncol, col = w - band * pl.ncol;
-    if (PEER) {
+    const int band = wid / pl.ncol, col = wid - band * pl.ncol;
+    if (!PEER) {
+        int bs, be;
+        march_band_rows(pl, band, &bs, &be);
+        if (be < bs) return;
+        if (pl.band_land && pl.band_land[wid]) return;  // every output cell of this warp's band is land
+        march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, false>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, -1);
+        return;
+    }
 #pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            if (peer.out[side][0] == nullptr || band != (side ? pl.nbands - 1 : 0)) continue;
-            // boundary strip of this side: compute, push, publish -- before my own band
-            const int ss = side == 0 ? peer.lo0 : peer.hi0, se = side == 0 ? peer.lo1 : peer.hi1;
-            if (se >= ss) march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, true>(g, a, src, peer, smem_raw, lane, wib, col, ss, se, side);
-            __threadfence_system();  // every lane: its stores into the neighbour's memory are visible system-wide ...
-            __syncwarp();
-            if (lane == 0) {          // ... before the last strip warp of this side publishes the step counter there
-                unsigned *cnt = side ? peer.count[1] : peer.count[0];
-                if (atomicAdd(cnt, 1u) == (unsigned)pl.ncol - 1u) {
-                    *cnt = 0;
-                    __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long *>(side ? peer.ready[1] : peer.ready[0]) = peer.tick;
-                }
+    for (int side = 0; side < 2; ++side) {
+        if (peer.out[side][0] == nullptr || band != (side ? pl.nbands - 1 : 0)) continue;
+        const int bs = side == 0 ? peer.lo0 : peer.hi0, be = side == 0 ? peer.lo1 : peer.hi1;
+        if (be >= bs && !(peer.dbg & 1)) {
+            // the strip reads my halo rows of the current state: the neighbour's push of the previous step
+            if (lane == 0) {
+                const volatile unsigned long long *f = side ? peer.ready_in[1] : peer.ready_in[0];
+                while (*f + 1 < peer.tick) __nanosleep(64);
             }
             __syncwarp();
         }
+        if (be >= bs) march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, true>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, side);
+        __threadfence_system();  // every lane: its stores into the neighbour's memory are visible system-wide ...
+        __syncwarp();
+        if (lane == 0) {          // ... before the last strip warp of this side publishes the step counter there
+            unsigned *cnt = side ? peer.count[1] : peer.count[0];
+            if (atomicAdd(cnt, 1u) == (unsigned)pl.ncol - 1u) {
+                *cnt = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long *>(side ? peer.ready[1] : peer.ready[0]) = peer.tick;
+            }
+        }
+        __syncwarp();
     }
-    int bs, be;
-    march_band_rows(pl, band, &bs, &be);
-    if (be < bs) return;
-    if (pl.band_land && pl.band_land[w]) return;  // every output cell of this warp's band is land
-    march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, false>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, -1);
 }
 
 
