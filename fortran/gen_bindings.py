@@ -22,6 +22,8 @@ STRUCTS = {"swcu_dims", "swcu_params", "swh_basin"}
 OUT_SCALARS = {
     ("swcu_synchronize", "bad_cells"): "integer(c_long), intent(out)",
     ("swcu_timer_stop", "elapsed_ms"): "real(c_float), intent(out)",
+    ("swcu_march_band_rows", "first"): "integer(c_int), intent(out)",
+    ("swcu_march_band_rows", "last"): "integer(c_int), intent(out)",
     ("swcu_halo_plan", "send_row"): "integer(c_int), intent(out)",
     ("swcu_halo_plan", "recv_row"): "integer(c_int), intent(out)",
     ("swh_uniform_split", "start"): "integer(c_int), intent(out)",

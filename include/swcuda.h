@@ -308,6 +308,11 @@ int swcu_comm_destroy(swcu_ctx *ctx);
  * (array row of reference row n is n - bnd_y1; get_boundary_points_of_block /
  * get_halo_points_of_block, core/decomposition.f90:94-154, 230-290, widened to nrows). */
 int swcu_halo_plan(const swcu_dims *dims, int nrows, int side, int *send_row, int *recv_row);
+/* The row bookkeeping of k_march, exposed so it can be tested without a GPU: rows [*first .. *last] (inclusive;
+ * empty if *last < *first) of band `band` when rows [n0 .. n1] are cut into `nbands` bands of which the last
+ * `late_bands` are `late_cut` rows shorter than the others (the bands whose CTAs start late beside a concurrent
+ * strip launch).  The bands tile [n0 .. n1] exactly once, in order. */
+int swcu_march_band_rows(int n0, int n1, int nbands, int late_bands, int late_cut, int band, int *first, int *last);
 /* One explicit halo exchange of a field (all ranks call it): the analogue of
  * `call sync(domain, data2d)` (shared/mpp/sync.f90:541-556) for init-time use.  Over a communicator or
  * in-process links; SWCU_ERR_STATE on a block that uses peer memory (which carries only the step's arrays). */

@@ -123,6 +123,7 @@ _SIGNATURES = {
     "swcu_version": [],
     "swcu_device_count": [],
     "swcu_widen_halos": [_P],
+    "swcu_march_band_rows": [_I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)],
     "swh_masks": [C.POINTER(SwhBasin), _DIMS] + [_P] * 8,
     "swh_metrics": [C.POINTER(SwhBasin), _DIMS] + [_P] * 9,
     "swh_gaussian": [_DIMS, _P, _P, _D, _I, _I],

@@ -207,7 +207,7 @@ struct swcu_ctx {
         std::vector<void *> opened;
     } peer[2];                                // 0 = below (rank-1), 1 = above (rank+1)
     unsigned long long *flags = nullptr;      // mine: READY lo/hi, FREE lo/hi, READY_FF lo/hi
-    unsigned *push_count = nullptr;           // counters: [0,1] k_push_halo, [2,3] strip warps of k_march
+    unsigned *push_count = nullptr;           // counters: [0,1] k_push_halo, [2,3] strip warps of k_march, [5] timeout flag
     double *set_ptr[2][8] = {};               // my planes in export order
     int cur_set = 0;                          // set_ptr[cur_set] holds the current state
     // per-row metric tables (FUSED): rebuilt after a metric upload, used when all arrays are row-constant
@@ -786,6 +786,7 @@ int fused_main(swcu_ctx *c, double tau)
         }
         mp.tick = tick;
         mp.dbg = dbg;
+        mp.timeout = reinterpret_cast<int *>(c->push_count + 5);
         // strips: band 0's warps take the lower strip, the last band's the upper one; no band rows
         MarchPlan sp;
         march_plan(g, ns, ns - 1, c->march_warps, &sp);
@@ -1448,6 +1449,15 @@ int swcu_synchronize(swcu_ctx *c, long *bad_cells)
     SWCU_CUDA(cudaStreamSynchronize(c->st));
     SWCU_CUDA(cudaStreamSynchronize(c->comm_st));
     SWCU_CUDA(cudaStreamSynchronize(c->bnd_st));
+    if (c->push_count && (c->peer[0].on || c->peer[1].on)) {   // did a strip warp give up waiting for a neighbour?
+        int to = 0;
+        SWCU_CUDA(cudaMemcpy(&to, c->push_count + 5, sizeof(int), cudaMemcpyDeviceToHost));
+        if (to) {
+            SWCU_CUDA(cudaMemset(c->push_count + 5, 0, sizeof(int)));
+            set_error("a neighbouring block never signalled its halo rows / free buffers (peer-memory path timed out)");
+            return SWCU_ERR_STATE;
+        }
+    }
     const long bad = *c->bad_host;
     if (bad_cells) *bad_cells = bad;
     if (bad) { set_error("check_ssh_err: %ld sea cells with |ssh| >= 1e4 or NaN", bad); return SWCU_ERR_BLOWUP; }
@@ -1861,6 +1871,19 @@ int swcu_peer_attach(swcu_ctx *c, int side, const void *blob)
         const unsigned long long v = (unsigned long long)c->steps_done;
         SWCU_CUDA(cudaMemcpy(c->flags + side, &v, sizeof(v), cudaMemcpyHostToDevice));
     }
+    return SWCU_OK;
+}
+
+int swcu_march_band_rows(int n0, int n1, int nbands, int late_bands, int late_cut, int band, int *first, int *last)
+{
+    if (!first || !last || nbands < 1 || band < 0 || band >= nbands || late_bands < 0 || late_bands > nbands || late_cut < 0) {
+        set_error("bad band arguments");
+        return SWCU_ERR_ARG;
+    }
+    MarchPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.n0 = n0; pl.n1 = n1; pl.nbands = nbands; pl.late_hi = late_bands; pl.late_cut = late_cut;
+    march_band_rows(pl, band, first, last);
     return SWCU_OK;
 }
 

@@ -67,6 +67,7 @@ struct MarchPeer {
     const unsigned long long *free_[2];  // my "your rows in my write buffers may be overwritten" words
     unsigned long long tick;
     unsigned *count[2];                  // strip-warp counters (zero between launches)
+    int *timeout;                        // raised when a neighbour's flag never arrived (device int)
     int dbg;                             // timing experiments only (SWCU_PEER_DBG): 1 = no wait for "free", 2 = no peer stores
 };
 // rows [*bs .. *be] of band `band`

@@ -299,11 +299,11 @@ int step_launch(const StepMaps &maps, const Geo &g, const FusedArgs &a, int n0, 
     static unsigned long long attr_set = 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!(attr_set >> (dev & 63) & 1ull)) {
+    if (!(__atomic_load_n(&attr_set, __ATOMIC_ACQUIRE) >> (dev & 63) & 1ull)) {   // contexts may step from several host threads
         cudaError_t e = cudaFuncSetAttribute(k_step<CFG, T, L, R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)CFG::SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_step)");
-        attr_set |= 1ull << (dev & 63);
+        __atomic_fetch_or(&attr_set, 1ull << (dev & 63), __ATOMIC_RELEASE);
     }
     const dim3 grid((unsigned)((g.nx_end - g.nx_start + TX) / TX), (unsigned)((n1 - n0 + CFG::TY) / CFG::TY), 1);
     k_step<CFG, T, L, R, D><<<grid, CFG::THREADS, CFG::SMEM, st>>>(maps, g, a, n0, n1);

@@ -127,6 +127,18 @@ __device__ __forceinline__ void st_if(bool pred, double *ptr, double v)
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %0, 0; @p st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(ptr), "d"(v));
 }
 
+// Waits until the flag word (written by a neighbouring GPU over NVLink) reaches `want`.  A neighbour that never
+// gets there (a dead process) must not hang this GPU for ever: after ~2^26 polls (several seconds) the wait gives
+// up and raises *timeout, which swcu_synchronize reports as an error; the step's results are then invalid.
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long want, int *timeout)
+{
+    const volatile unsigned long long *f = flag;
+    for (unsigned n = 0; *f < want; ++n) {
+        if (n >> 26) { atomicExch(timeout, 1); break; }
+        __nanosleep(64);
+    }
+}
+
 struct MarchIn {
     const double *in[NARR];  // ssh sshp u up v vp hhq_rest mu
 };
@@ -351,10 +363,7 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
             // boundary strip: the same cells go straight into the neighbour's halo rows (NVLink stores).  The
             // neighbour must have declared those rows of its write buffers free for this step.
             if (b == bs && !(peer.dbg & 1)) {
-                if (lane == 0) {
-                    const volatile unsigned long long *f = side ? peer.free_[1] : peer.free_[0];
-                    while (*f < peer.tick) __nanosleep(64);
-                }
+                if (lane == 0) spin_until(side ? peer.free_[1] : peer.free_[0], peer.tick, peer.timeout);
                 __syncwarp();
                 __threadfence_system();
             }
@@ -421,10 +430,7 @@ k_march(Geo g, FusedArgs a, MarchIn src, MarchPlan pl, MarchPeer peer)
         const int bs = side == 0 ? peer.lo0 : peer.hi0, be = side == 0 ? peer.lo1 : peer.hi1;
         if (be >= bs && !(peer.dbg & 1)) {
             // the strip reads my halo rows of the current state: the neighbour's push of the previous step
-            if (lane == 0) {
-                const volatile unsigned long long *f = side ? peer.ready_in[1] : peer.ready_in[0];
-                while (*f + 1 < peer.tick) __nanosleep(64);
-            }
+            if (lane == 0) spin_until(side ? peer.ready_in[1] : peer.ready_in[0], peer.tick - 1, peer.timeout);
             __syncwarp();
         }
         if (be >= bs) march_warp<TRANS, LAT, FFS, HAS_RHS, HAS_RDISS, true>(g, a, src, peer, smem_raw, lane, wib, col, bs, be, side);

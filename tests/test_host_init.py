@@ -181,3 +181,35 @@ def test_balanced_slabs(swlib):
                 assert max(bal) < 0.8 * max(uni), (bal, uni)          # the land-heavy slab got more rows
     ds = [model.balanced_slab_dims(nx, ny, 5, r, None) for r in range(5)]       # no mask: near-uniform
     assert max(d.ny_end - d.ny_start for d in ds) - min(d.ny_end - d.ny_start for d in ds) <= 8
+
+
+def test_march_bands_tile_the_rows_exactly_once(swlib):
+    """k_march's row bookkeeping (csrc/sw_fused.h march_band_rows): for any row range, band count and number /
+    size of shortened late bands, the bands are consecutive, non-overlapping, cover [n0 .. n1] exactly, and the
+    late bands are late_cut rows shorter than the others (to within the rounding of the division)."""
+    import ctypes as C
+    import random
+    rnd = random.Random(20241018)
+    cases = [(3, 2050, 16, 1, 24), (3, 2050, 16, 2, 24), (3, 2050, 16, 0, 0), (3, 4, 1, 0, 0), (5, 5, 3, 1, 0),
+             (3, 8194, 64, 0, 0), (7, 1030, 9, 2, 10)]
+    for _ in range(300):
+        n0 = rnd.randint(1, 50); rows = rnd.randint(1, 5000); nb = rnd.randint(1, 80)
+        late = rnd.randint(0, min(nb, 3)); cut = rnd.choice([0, 1, 8, 24, 40])
+        if late and rows // nb <= 2 * cut:
+            cut = 0        # the library only shortens bands that are comfortably longer than the cut
+        cases.append((n0, n0 + rows - 1, nb, late, cut))
+    for n0, n1, nb, late, cut in cases:
+        nxt = n0
+        lens = []
+        for b in range(nb):
+            f, l = C.c_int(), C.c_int()
+            assert swlib.swcu_march_band_rows(n0, n1, nb, late, cut, b, C.byref(f), C.byref(l)) == 0
+            assert f.value == nxt and l.value >= f.value - 1, (n0, n1, nb, late, cut, b, f.value, l.value)
+            nxt = l.value + 1
+            lens.append(l.value - f.value + 1)
+        assert nxt == n1 + 1, (n0, n1, nb, late, cut)
+        if late and cut and nb > late:
+            normal, short = lens[:nb - late], lens[nb - late:]
+            assert max(short) <= min(normal) - cut + 2 and min(short) >= max(normal) - cut - 2, (n0, n1, nb, late, cut, lens)
+    f, l = C.c_int(), C.c_int()
+    assert swlib.swcu_march_band_rows(1, 10, 4, 5, 0, 0, C.byref(f), C.byref(l)) != 0     # more late bands than bands
