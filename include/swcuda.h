@@ -178,8 +178,8 @@ enum swcu_field {
 
 /* step structure */
 #define SWCU_MODE_REFERENCE 0 /* the reference's 11-kernel sequence, one launch per kernel (K1..K11) */
-#define SWCU_MODE_FUSED 1     /* the whole step in ONE launch (TMA-tiled; K1..K11 fused), or prep + update
-                               * launches when the grid's metrics vary along x; + one launch for the tracer */
+#define SWCU_MODE_FUSED 1     /* the whole step in ONE launch (K1..K11 fused: k_march, or k_step with "exact" = 1), or
+                               * prep + update launches when the grid's metrics vary along x; + one launch per tracer */
 
 typedef struct swcu_params {
     int full_free_surface, trans_terms, ksw_lat; /* sw.par 1-3 (configs/sw.f90:34-36) */
