@@ -15,13 +15,16 @@
 //     the east / west neighbours by warp shuffles;
 //   - the row's coefficients (a 256-byte table row, sw_fast.cuh) travel through the same ring and are read
 //     with broadcast 16-byte loads (as plain global loads their L2 latency was 59 % of all stall samples:
-//     profiles/r02_march_v1.txt).
-// Per cell this costs ~140 fp64 instructions, ~13 shared-memory loads and ~23 shuffles, against ~490
-// fp64 instructions and ~160 shared-memory accesses of the bitwise kernel k_step.
+//     profiles/r02_march_v1_coef_ldg.txt).
+// Per cell-row this costs 118 fp64 instructions, ~28 shared-memory loads of inputs, 19 of coefficients and 23
+// shuffles, against ~490 fp64 instructions and ~160 shared-memory accesses of the bitwise kernel k_step.
 //
 // Launch geometry: ncol = ceil(columns / 28) warp columns x nbands bands of rows, nbands chosen so
-// that all warps are resident at once (one wave, equal work).  Boundary strips of a multi-GPU step
-// are the same kernel on 2 rows (NCCL path) or part of the launch (peer memory: MarchPeer).
+// that all warps are resident at once (one wave, equal work); with enough land, 128-row bands whose all-land
+// members exit at once.  Boundary strips of a multi-GPU step are the same kernel on 2 rows (NCCL path) or, over
+// peer memory, the PEER instantiation: a small concurrent launch that also stores the strips into the
+// neighbours' halo rows and publishes the step counter (MarchPeer, sw_fused.h).  profiles/r02_notes.md has the
+// measurements behind every choice in this file.
 #include <cstring>
 
 #include "sw_fast.cuh"
@@ -218,9 +221,9 @@ __device__ __forceinline__ void march_warp(const Geo &g, const FusedArgs &a, con
     for (int j = 0; j < RING; ++j) issue_row(r_first + j, j);
 
     // ---- state.  Raw inputs are re-read from the ring where they are needed (rows b .. b+2 stay there for the
-    // whole iteration); only COMPUTED values live across iterations.  They sit in two banks that swap roles
-    // every row (the loop is unrolled by two), so nothing is copied from register to register:
-    // in the iteration that outputs row b, bank X holds row b's values and bank Y receives row b+1's.
+    // whole iteration); only COMPUTED values live across iterations, in two banks: in the iteration that outputs
+    // row b, bank X holds row b's values and bank Y receives row b+1's.  (With SWCU_MARCH_UNROLL2 the banks swap
+    // roles every row and nothing is copied; the default plain loop copies Y to X after every row and is faster.)
     struct Bank {
         AOut A;            // stage A of the bank's row
         double q, qm, s;   // thickness at T points of the row ABOVE the bank's row: unmasked, masked, qm_c + qm_e
