@@ -89,3 +89,24 @@ def test_tracer_transport_1000_steps():
     for n in STATE + ("ff1", "ff1p"):
         assert rel(o.get(n), f.get(n)) <= 1e-13, (n, rel(o.get(n), f.get(n)))
     assert np.array_equal(o.get("ff1")[lu < 0.5], f.get("ff1")[lu < 0.5])
+
+
+def test_mass_conservation_and_bounds_in_tolerance_arithmetic():
+    """Size-independent properties of the re-associated scheme (the ones the GPU tests use at the BASELINE sizes):
+    K1 stays in flux form -- the SAME volume flux u*dyh*hhu leaves one cell and enters its neighbour -- so the
+    volume sum(ssh * real4(dx*dy)) over the sea is conserved to rounding; land cells never change; |ssh| bounded."""
+    nx, ny = 120, 90
+    mask = basins.island_mask(nx, ny)
+    cfg = make_config(nx, ny, keep_mu=1)
+    o = OracleModel(cfg, mask)
+    f = FastHostModel(o, cfg)
+    lu = o.get("lu")
+    area = (o.get("dx") * o.get("dy")).astype(np.float64) * lu
+    v0 = float((f.get("ssh") * area).sum())
+    ssh0 = f.get("ssh").copy()
+    assert f.step(500) == 0
+    v1 = float((f.get("ssh") * area).sum())
+    assert abs(v1 - v0) <= 1e-12 * abs(v0)
+    assert np.array_equal(f.get("ssh")[lu < 0.5], ssh0[lu < 0.5])
+    assert np.isfinite(f.get("ssh")).all() and np.abs(f.get("ssh")).max() <= np.abs(ssh0).max() * 1.0000001
+    assert np.abs(f.get("ubrtr")).max() > 0
