@@ -759,8 +759,14 @@ int fused_main(swcu_ctx *c, double tau)
         // high-priority stream.  No stream ever waits for a neighbour: the strip warps do, inside the kernel.
         const unsigned long long tick = (unsigned long long)c->steps_done + 1;
         RC(write_value_load());
-        int dbg = 0;
-        if (const char *e = getenv("SWCU_PEER_DBG")) dbg = atoi(e);
+        // Bits for timing experiments only (1: strip warps do not wait for the neighbours' flags, 2: no stores into
+        // the neighbours' memory, 4: no "free" signal / tracer wait) -- each of them breaks the exchange, so they
+        // are read only from a build-time switch, never from the environment of a production run.
+#ifdef SWCU_ENABLE_PEER_DBG
+        int dbg = getenv("SWCU_PEER_DBG") ? atoi(getenv("SWCU_PEER_DBG")) : 0;
+#else
+        const int dbg = 0;
+#endif
         // everything that read my write buffers (the previous step, an upload's copy) is on the compute stream
         SWCU_CUDA(cudaEventRecord(c->ev_start, c->st));
         SWCU_CUDA(cudaStreamWaitEvent(c->bnd_st, c->ev_start, 0));
